@@ -1,0 +1,81 @@
+// VideoProcessor.h -- drop-in replacement of the reference's include/VideoProcessor.h for the
+// VPP hot path.  Same enum values, same option structs, same VideoProcessor member signatures
+// (reference include/VideoProcessor.h:20-149), so TensorStream::getFrame
+// (src/Wrappers/WrapperPython.cpp:312, src/Wrappers/WrapperC.cpp:291) and tests written against
+// the reference (tests/src/VPPTests.cpp) compile unchanged -- but Convert() runs ONE fused
+// sm_100a kernel through the C ABI in tsvpp.h instead of crop + resize + colour kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "Common.h"
+#include "tsvpp_avframe.h"
+
+struct TsvppContext;
+
+enum FourCC { Y800 = 0, RGB24, BGR24, NV12, UYVY, YUV444, HSV };
+enum Planes { PLANAR = 0, MERGED };
+enum ResizeType { NEAREST = 0, BILINEAR, BICUBIC, AREA };
+
+struct ColorOptions {
+    ColorOptions(FourCC fourCC = FourCC::RGB24)
+        : normalization(fourCC == FourCC::HSV), planesPos(Planes::MERGED), dstFourCC(fourCC) {}
+    bool normalization;
+    Planes planesPos;
+    FourCC dstFourCC;
+};
+
+struct ResizeOptions {
+    ResizeOptions(int w = 0, int h = 0) : width((unsigned)w), height((unsigned)h), type(ResizeType::NEAREST) {}
+    unsigned int width;  // 0 => keep source size
+    unsigned int height;
+    ResizeType type;
+};
+
+struct CropOptions {
+    CropOptions(std::tuple<int, int> lt = {0, 0}, std::tuple<int, int> rb = {0, 0})
+        : leftTopCorner(lt), rightBottomCorner(rb) {}
+    std::tuple<int, int> leftTopCorner;  // zero-area box => no crop
+    std::tuple<int, int> rightBottomCorner;
+};
+
+struct FrameParameters {
+    FrameParameters(ResizeOptions r = ResizeOptions(), ColorOptions c = ColorOptions(), CropOptions k = CropOptions())
+        : resize(r), color(c), crop(k) {}
+    ResizeOptions resize;
+    ColorOptions color;
+    CropOptions crop;
+};
+
+float channelsByFourCC(FourCC fourCC);
+float channelsByFourCC(std::string fourCC);
+
+class VideoProcessor {
+public:
+    int Init(std::shared_ptr<Logger> logger, uint8_t maxConsumers = 5, bool _enableDumps = false);
+    // input: NV12 in device memory (data[0]=Y, data[1]=UV, linesize[0..1], width, height).
+    // output->opaque receives a fresh device buffer (stream-ordered allocation, cudaFree-able
+    // by the caller exactly like the reference's), output->width/height the final size.
+    int Convert(AVFrame *input, AVFrame *output, FrameParameters &options, std::string consumerName);
+    template <class T>
+    int DumpFrame(T *output, FrameParameters options, std::shared_ptr<FILE> dumpFile);
+    void Close();
+    ~VideoProcessor();
+
+private:
+    bool enableDumps = false;
+    int device = 0;
+    TsvppContext *ctx = nullptr;
+    std::vector<std::pair<std::string, cudaStream_t>> streamArr;  // one stream per consumer
+    std::mutex streamSync;
+    std::mutex dumpSync;
+    bool isClosed = true;
+    std::shared_ptr<Logger> logger;
+};

@@ -199,6 +199,17 @@ void vpo_set_bicubic_fma(int on) { g_bicubic_fma = on; }
 void vpo_bicubic_weights(double w, double c[4]) {
     const double a = -0.75;
     double w2 = pow(w, 2), w3 = pow(w, 3);
+    if (g_bicubic_fma) {
+        /* as compiled for sm_100a (cuobjdump -sass of the unmodified reference, a folded to
+         * -0.75): t=w2*1.5; q=w3*-0.75; c0=fma(w,-.75,t)+q; c1=fma(w3,1.25,fma(w2,-2.25,1));
+         * c2=fma(w3,-1.25,fma(w,.75,t)); c3=fma(w2,-.75,-q) */
+        double t = w2 * 1.5, q = w3 * -0.75;
+        c[0] = fma(w, -0.75, t) + q;
+        c[1] = fma(w3, 1.25, fma(w2, -2.25, 1.0));
+        c[2] = fma(w3, -1.25, fma(w, 0.75, t));
+        c[3] = fma(w2, -0.75, -q);
+        return;
+    }
     c[0] = a * w - 2 * a * w2 + a * w3;
     c[1] = 1 - (a + 3) * w2 + (a + 2) * w3;
     c[2] = -a * w + (2 * a + 3) * w2 - (a + 2) * w3;
@@ -207,8 +218,9 @@ void vpo_bicubic_weights(double w, double c[4]) {
 
 static inline double dot4(const double c[4], double d0, double d1, double d2, double d3) {
     if (g_bicubic_fma) {
-        double s = c[0] * d0;
-        s = fma(c[1], d1, s);
+        /* SASS order: DMUL c1*d1; DFMA c0,d0; DFMA c2,d2; DFMA c3,d3 */
+        double s = c[1] * d1;
+        s = fma(c[0], d0, s);
         s = fma(c[2], d2, s);
         s = fma(c[3], d3, s);
         return s;

@@ -1,0 +1,55 @@
+"""In-tree build of the native library (nvcc, sm_100a only).
+
+  python -m tensor_stream_b200.build        # builds tensor_stream_b200/libtsvpp.so
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.  nvcc
+cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libtsvpp.so")
+
+SOURCES = ["vpp_kernels.cu", "tsvpp_capi.cpp", "VideoProcessor.cpp"]
+HEADERS = ["vpp_plan.h", "vpp_launch.h", "../../include/tsvpp.h", "../../include/VideoProcessor.h",
+           "../../include/tsvpp_avframe.h"]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-I", os.path.join(HERE, "..", "include"),
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    objs = []
+    for s in srcs:
+        o = os.path.join(CSRC, os.path.basename(s) + ".o")
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        if s.endswith(".cpp"):
+            cmd.insert(1, "-x")
+            cmd.insert(2, "cu")
+        subprocess.check_call(cmd)
+        objs.append(o)
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB] + objs + ["-lcuda"])
+    for o in objs:
+        os.remove(o)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,894 @@
+// tsvpp_capi.cpp -- plan builder, context and the C ABI of include/tsvpp.h.
+//
+// Host-side logic of the hot path: the dispatch rules of the reference's
+// VideoProcessor::Convert (src/VideoProcessor.cpp:106-143) and the per-pixel coordinate / weight
+// formulas of its resize kernels (src/Resize.cu:180-357), evaluated ONCE per (geometry, params)
+// into tables instead of per pixel per frame.  All float math here mirrors the device arithmetic
+// of the reference bit for bit: fmaf() where nvcc contracted, plain IEEE ops elsewhere; this file
+// is compiled with -ffp-contract=off.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tsvpp.h"
+#include "vpp_launch.h"
+#include "vpp_plan.h"
+
+using namespace tsvpp;
+
+namespace {
+
+#define TSVPP_CUDA(expr)                                  \
+    do {                                                  \
+        cudaError_t e_ = (expr);                          \
+        if (e_ != cudaSuccess) return (int)e_;            \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int env_int(const char *name, int dflt) {
+    const char *s = std::getenv(name);
+    return (s && *s) ? std::atoi(s) : dflt;
+}
+
+// ---------------------------------------------------------------------------------------
+// Dispatch rules -- reference src/VideoProcessor.cpp:106-135
+// ---------------------------------------------------------------------------------------
+struct Geometry {
+    bool crop = false, resize = false;
+    int x0 = 0, y0 = 0;  // crop origin in the source
+    int sw = 0, sh = 0;  // working (post-crop) size
+    int dw = 0, dh = 0;  // final size
+};
+
+Geometry resolve_geometry(int W, int H, const TsvppParams &p) {
+    Geometry g;
+    g.sw = W;
+    g.sh = H;
+    const int cw = p.crop_x1 - p.crop_x0, ch = p.crop_y1 - p.crop_y0;
+    if (cw > 0 && ch > 0 && cw < W && ch < H) {  // VideoProcessor.cpp:109 (both strictly smaller)
+        g.crop = true;
+        g.x0 = p.crop_x0;
+        g.y0 = p.crop_y0;
+        g.sw = cw;
+        g.sh = ch;
+    }
+    g.dw = g.sw;
+    g.dh = g.sh;
+    if (p.dst_width && p.dst_height && (p.dst_width != g.sw || p.dst_height != g.sh)) {  // :118-124
+        g.resize = true;
+        g.dw = p.dst_width;
+        g.dh = p.dst_height;
+    }
+    return g;
+}
+
+// channelsByFourCC -- reference src/VideoProcessor.cpp:4-14
+float channels_of(int fourcc) {
+    if (fourcc == TSVPP_Y800) return 1.f;
+    if (fourcc == TSVPP_UYVY) return 2.f;
+    if (fourcc == TSVPP_NV12) return 1.5f;
+    return 3.f;
+}
+
+int out_kind_of(const TsvppParams &p) {
+    const bool f32 = p.normalization != 0;
+    switch (p.fourcc) {
+        case TSVPP_RGB24:
+        case TSVPP_BGR24:
+            if (p.planes == TSVPP_PLANAR) return f32 ? OUT_RGB_PLANAR_F32 : OUT_RGB_PLANAR_U8;
+            return f32 ? OUT_RGB_MERGED_F32 : OUT_RGB_MERGED_U8;
+        case TSVPP_Y800: return f32 ? OUT_Y800_F32 : OUT_Y800_U8;
+        case TSVPP_NV12: return f32 ? OUT_NV12_F32 : OUT_NV12_U8;
+        case TSVPP_HSV: return OUT_HSV_F32;  // always float, always merged (ColorConversion.cu:360-372)
+        default: return -1;
+    }
+}
+
+// reference src/Resize.cu:359-386 (generateResizePattern); rows are ceil(scale) floats wide,
+// surplus entries dropped as the kernel never reads them (Resize.cu:162-163).
+bool area_pattern(float scale, std::vector<float> &out, int &rows) {
+    const int stride = (int)std::ceil(scale);
+    const float eps = std::numeric_limits<float>::epsilon();
+    int id = 0;
+    float rest = 0;
+    out.clear();
+    while ((float)id * scale == 0 || ((float)id * scale - (float)(int)((float)id * scale) > eps)) {
+        if (id >= (1 << 16)) return false;
+        out.resize((size_t)(id + 1) * stride, 0.f);
+        float *row = out.data() + (size_t)id * stride;
+        float dyn = scale;
+        int n = 0;
+        if (rest != 0) {
+            if (n < stride) row[n] = rest;
+            n++;
+            dyn -= rest;
+        }
+        while (dyn - 1 > 0) {
+            if (n < stride) row[n] = 1;
+            n++;
+            dyn -= 1.0f;
+        }
+        if (dyn > eps) {
+            if (n < stride) row[n] = dyn;
+            n++;
+            rest = 1 - dyn;
+        }
+        id++;
+    }
+    rows = id;
+    return true;
+}
+
+// One axis of the resampling: for output index k, the integer source coordinate, the fractional
+// weight and (bicubic) the double weight, exactly as the reference kernels compute them.
+struct AxisSample {
+    int pos = 0;
+    float w = 0.f;
+    double wd = 0.0;
+};
+
+AxisSample axis_sample(int rs_api, bool area_down, bool identity, int k, float ratio, int src_len) {
+    AxisSample a;
+    if (identity) {
+        a.pos = k;
+        return a;
+    }
+    switch (rs_api) {
+        case TSVPP_NEAREST:  // Resize.cu:250-251
+            a.pos = (int)(ratio * (float)(unsigned)k);
+            break;
+        case TSVPP_BILINEAR: {  // Resize.cu:277-303
+            const float f = fmaf((float)(unsigned)k + 0.5f, ratio, -0.5f);
+            int x = (int)floorf(f);
+            float w = f - (float)x;
+            if (x < 0) { x = 0; w = 0; }
+            if (x > src_len - 1) { x = src_len - 1; w = 0; }
+            a.pos = x;
+            a.w = w;
+        } break;
+        case TSVPP_BICUBIC: {  // Resize.cu:322-348: f32 coordinate (FMA), widened to double
+            const double f = (double)fmaf((float)(unsigned)k + 0.5f, ratio, -0.5f);
+            int x = (int)std::floor(f);
+            double w = f - x;
+            if (x < 0) { x = 0; w = 0; }
+            if (x > src_len - 1) { x = src_len - 1; w = 0; }
+            a.pos = x;
+            a.wd = w;
+        } break;
+        case TSVPP_AREA:
+            if (area_down) {  // Resize.cu:187-193
+                a.pos = (int)floorf((float)(int)(ratio * (float)(unsigned)k));
+            } else {  // Resize.cu:220-232
+                const int x = (int)floorf(ratio * (float)(unsigned)k);
+                float w = (float)(unsigned)(k + 1) - (float)(x + 1) / ratio;
+                if (w <= 0) w = 0; else w = w - floorf(w);
+                a.pos = x;
+                a.w = w;
+            }
+            break;
+    }
+    return a;
+}
+
+// taps of one sample along one axis (positions in the working image; stride 1 or 2)
+// bilinear -- Resize.cu:7-10; bicubic -- Resize.cu:32-43
+void bilinear_taps(int X, int diff, int len, int t[2]) {
+    int d = diff;
+    if ((float)X + (float)d >= (float)len) d = 0;
+    t[0] = X;
+    t[1] = X + d;
+}
+void bicubic_taps(int X, int diff, int len, int t[4]) {
+    int d = diff, dtop = diff;
+    if (X + d >= len) d = 0;
+    if (X + d * 2 >= len) d = 0;
+    if (X - dtop < 0) dtop = 0;
+    t[0] = X - dtop;
+    t[1] = X;
+    t[2] = X + d;
+    t[3] = X + 2 * d;
+}
+
+struct DeviceArena {
+    std::vector<unsigned char> host;
+    size_t add(const void *p, size_t bytes) {
+        const size_t off = (host.size() + 255) / 256 * 256;
+        host.resize(off + bytes);
+        if (bytes) std::memcpy(host.data() + off, p, bytes);
+        return off;
+    }
+};
+
+struct PlanKey {
+    int w, h, pitch_y, pitch_uv, bulk;
+    TsvppParams p;
+    bool operator<(const PlanKey &o) const { return std::memcmp(this, &o, sizeof(PlanKey)) < 0; }
+};
+
+struct Plan {
+    PlanDev dev{};
+    int rs = 0, ok = 0;
+    bool bulk = true;
+    size_t smem = 0;
+    int ctas_per_sm = 1;
+    int out_w = 0, out_h = 0;
+    size_t out_elems = 0;
+    int elem_size = 1;
+    int vec_ok_geom = 0;  // dw % 4 == 0
+    void *dev_tables = nullptr;
+    std::string desc;
+    ~Plan() {
+        if (dev_tables) cudaFree(dev_tables);
+    }
+};
+
+}  // namespace
+
+struct TsvppContext {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 227 * 1024;
+    std::mutex mu;
+    std::map<PlanKey, std::unique_ptr<Plan>> plans;
+    std::atomic<unsigned long long> launches{0};
+    // descriptor ring for tsvpp_convert_batch (pinned host + device), guarded by events
+    static constexpr int kRing = 8;
+    FrameDev *ring_host[kRing] = {};
+    FrameDev *ring_dev[kRing] = {};
+    cudaEvent_t ring_ev[kRing] = {};
+    int ring_cap[kRing] = {};
+    int ring_next = 0;
+    // host-buffer path
+    cudaStream_t hstream[2] = {};
+    unsigned char *stage_in[2] = {};
+    unsigned char *stage_out[2] = {};
+    size_t stage_in_cap[2] = {}, stage_out_cap[2] = {};
+    cudaEvent_t hev[2] = {};
+};
+
+struct TsvppBatch {
+    TsvppContext *ctx = nullptr;
+    Plan *plan = nullptr;
+    FrameDev *frames_dev = nullptr;
+    int n = 0;
+    int vec_ok = 0;
+    int grid = 0;
+};
+
+namespace {
+
+int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in, const TsvppParams &p, bool bulk,
+               std::unique_ptr<Plan> &out) {
+    if (W <= 0 || H <= 0) return TSVPP_ERROR;
+    std::unique_ptr<Plan> pl(new Plan());
+    const Geometry g = resolve_geometry(W, H, p);
+    const int ok = out_kind_of(p);
+    if (ok < 0) {
+        if (p.fourcc == TSVPP_UYVY || p.fourcc == TSVPP_YUV444) return TSVPP_UNSUPPORTED;
+        return (int)cudaErrorMissingConfiguration;  // unknown FourCC, ColorConversion.cu:376
+    }
+    if (p.resize_type < TSVPP_NEAREST || p.resize_type > TSVPP_AREA) return TSVPP_UNSUPPORTED;
+
+    int pitch_y = pitch_y_in ? pitch_y_in : W;    // Resize.cu:420-421
+    int pitch_uv = pitch_uv_in ? pitch_uv_in : W;
+    const long plane_y = (long)pitch_y * H, plane_uv = (long)pitch_uv * (H / 2);
+    // colour conversion straight from the input frame indexes BOTH planes with linesize[0]
+    // (ColorConversion.cu:301); kept, including when the two pitches differ.
+    if (!g.crop && !g.resize) pitch_uv = pitch_y;
+
+    const bool identity = !g.resize;
+    const float xr = (float)g.sw / g.dw, yr = (float)g.sh / g.dh;  // Resize.cu:418-419
+    const bool area_down = g.resize && p.resize_type == TSVPP_AREA && xr > 1 && yr > 1;  // :436
+    int rs;
+    if (identity || p.resize_type == TSVPP_NEAREST) rs = RS_NEAREST;
+    else if (p.resize_type == TSVPP_BILINEAR) rs = RS_BILINEAR;
+    else if (p.resize_type == TSVPP_BICUBIC) rs = RS_BICUBIC;
+    else rs = area_down ? RS_AREA : RS_BILINEAR;
+
+    const bool need_uv = !(ok == OUT_Y800_U8 || ok == OUT_Y800_F32);
+    const int dw = g.dw, dh = g.dh;
+    const int cw2 = dw / 2, ch2 = dh / 2;  // chroma samples that exist (Resize.cu:305, i<dstH/2 && j<dstW/2)
+
+    // ---- pattern tables (AREA downscale) ----
+    std::vector<float> patx, paty;
+    int PX = 1, PY = 1;
+    int KX = 1, K = 1;
+    if (rs == RS_AREA) {
+        if (!area_pattern(xr, patx, PX) || !area_pattern(yr, paty, PY)) return TSVPP_UNSUPPORTED;
+        KX = (int)std::ceil(xr);
+        K = (int)std::ceil(yr);
+    } else if (rs == RS_BILINEAR) {
+        K = 2;
+    } else if (rs == RS_BICUBIC) {
+        K = 4;
+    }
+    const int ntap_x = (rs == RS_NEAREST) ? 1 : (rs == RS_BILINEAR) ? 2 : (rs == RS_BICUBIC) ? 4 : 1;
+
+    // ---- per-column samples (absolute byte positions inside a source row) ----
+    std::vector<AxisSample> xs(dw), ys(std::max(dh, 1));
+    for (int j = 0; j < dw; ++j) xs[j] = axis_sample(p.resize_type, area_down, identity, j, xr, g.sw);
+    for (int i = 0; i < dh; ++i) ys[i] = axis_sample(p.resize_type, area_down, identity, i, yr, g.sh);
+
+    // luma taps per column [dw][ntap_x], chroma taps per chroma byte [dw][ntap_x]; -1 = absent
+    std::vector<int> tap_l((size_t)dw * 4, 0), tap_c((size_t)dw * 4, 0);
+    std::vector<int> lo_l(dw), hi_l(dw), lo_c(dw, 0), hi_c(dw, 0);
+    const int row_bytes_max_y = pitch_y, row_bytes_max_uv = pitch_uv;
+    auto clamp_abs = [](int v, int hi) { return std::max(0, std::min(v, hi)); };
+    for (int j = 0; j < dw; ++j) {
+        int t[4] = {0, 0, 0, 0};
+        const int X = xs[j].pos;
+        if (rs == RS_NEAREST) t[0] = X;
+        else if (rs == RS_BILINEAR) bilinear_taps(X, 1, g.sw, t);
+        else if (rs == RS_BICUBIC) bicubic_taps(X, 1, g.sw, t);
+        else t[0] = X;
+        int lo = 1 << 30, hi = -1;
+        for (int k = 0; k < ntap_x; ++k) {
+            const int a = clamp_abs(g.x0 + t[k], row_bytes_max_y - 1);
+            tap_l[(size_t)j * 4 + k] = a;
+            lo = std::min(lo, a);
+            hi = std::max(hi, a);
+        }
+        if (rs == RS_AREA) hi = std::min(tap_l[(size_t)j * 4] + (KX - 1), row_bytes_max_y - 1);
+        lo_l[j] = lo;
+        hi_l[j] = hi;
+    }
+    if (need_uv) {
+        for (int b = 0; b < dw; ++b) {
+            const int cj = b >> 1, comp = b & 1;
+            if (cj >= cw2) {  // no chroma sample here: point at byte 0 of the segment
+                lo_c[b] = -1;
+                continue;
+            }
+            int t[4] = {0, 0, 0, 0};
+            const int X = 2 * xs[cj].pos + comp;  // Resize.cu:306-307: (2*x, 2*x+1) with xDiff=2
+            if (rs == RS_NEAREST) t[0] = X;
+            else if (rs == RS_BILINEAR) bilinear_taps(X, 2, g.sw, t);
+            else if (rs == RS_BICUBIC) bicubic_taps(X, 2, g.sw, t);
+            else t[0] = X;
+            int lo = 1 << 30, hi = -1;
+            for (int k = 0; k < ntap_x; ++k) {
+                const int a = clamp_abs(g.x0 + t[k], row_bytes_max_uv - 1);
+                tap_c[(size_t)b * 4 + k] = a;
+                lo = std::min(lo, a);
+                hi = std::max(hi, a);
+            }
+            if (rs == RS_AREA) hi = std::min(tap_c[(size_t)b * 4] + 2 * (KX - 1), row_bytes_max_uv - 1);
+            lo_c[b] = lo;
+            hi_c[b] = hi;
+        }
+    }
+
+    // ---- tiling and shared-memory budget ----
+    const int want_tw = env_int("TSVPP_TW", 256);
+    const int want_rp = env_int("TSVPP_RP", 2);
+    const int want_ns = env_int("TSVPP_STAGES", 0);
+    const size_t smem_cap = ctx->smem_optin;
+    int tw = 32, rp = 1, nstages = 1, ntiles = 1, slot_stride = 16;
+    std::vector<int> a0l, lenl, a0c, lenc;
+    bool found = false;
+    for (int cand_rp = std::min(2, std::max(1, want_rp)); cand_rp >= 1 && !found; --cand_rp) {
+        if (cand_rp == 2 && dh < 4) continue;
+        for (int cand = 256; cand >= 32 && !found; cand >>= 1) {
+            if (cand > want_tw) continue;
+            if (cand > 32 && cand >= 2 * round_up(dw, 32)) continue;  // don't over-size tiles for narrow outputs
+            const int nt = (dw + cand - 1) / cand;
+            std::vector<int> A0l(nt), Ll(nt), A0c(nt, 0), Lc(nt, 16);
+            int stride = 16;
+            for (int t = 0; t < nt; ++t) {
+                const int j0 = t * cand, j1 = std::min(dw, j0 + cand);
+                int lo = 1 << 30, hi = -1;
+                for (int j = j0; j < j1; ++j) {
+                    lo = std::min(lo, lo_l[j]);
+                    hi = std::max(hi, hi_l[j]);
+                }
+                A0l[t] = lo & ~15;
+                int need = hi + 1 - A0l[t];
+                Ll[t] = std::min(round_up(need, 16), round_up(pitch_y - A0l[t], 16));
+                stride = std::max(stride, round_up(need, 16));
+                if (need_uv) {
+                    lo = 1 << 30;
+                    hi = -1;
+                    for (int b = j0; b < j1; ++b) {
+                        if (lo_c[b] < 0) continue;
+                        lo = std::min(lo, lo_c[b]);
+                        hi = std::max(hi, hi_c[b]);
+                    }
+                    if (hi < 0) { lo = 0; hi = 0; }
+                    A0c[t] = lo & ~15;
+                    need = hi + 1 - A0c[t];
+                    Lc[t] = std::min(round_up(need, 16), round_up(pitch_uv - A0c[t], 16));
+                    stride = std::max(stride, round_up(need, 16));
+                }
+            }
+            const int nslots = (need_uv ? 3 : 2) * cand_rp * K;
+            const size_t stage = (size_t)nslots * stride;
+            const size_t fixed = 2 * (size_t)(3 * cand_rp * cand) + 8 * kMaxStages + 128;
+            int ns = 0;
+            if (!bulk) {
+                if (stage + fixed <= smem_cap) ns = 1;
+            } else {
+                const size_t budgets[3] = {72 * 1024, 110 * 1024, smem_cap};
+                for (size_t bgt : budgets) {
+                    if (bgt > smem_cap) bgt = smem_cap;
+                    if (bgt < fixed + stage) continue;
+                    const int n = (int)((bgt - fixed) / stage);
+                    if (n >= 3 || (bgt == smem_cap && n >= 1)) {
+                        ns = std::min(n, want_ns > 0 ? want_ns : 6);
+                        ns = std::min(ns, kMaxStages);
+                        break;
+                    }
+                }
+            }
+            if (ns >= 1) {
+                found = true;
+                tw = cand;
+                rp = cand_rp;
+                nstages = ns;
+                ntiles = nt;
+                slot_stride = stride;
+                a0l = A0l; lenl = Ll; a0c = A0c; lenc = Lc;
+            }
+        }
+    }
+    if (!found) return TSVPP_UNSUPPORTED;  // taps of one strip do not fit in shared memory
+
+    const int nstrips = (dh + 2 * rp - 1) / (2 * rp);
+    const int nrows_l = nstrips * 2 * rp, nrows_c = nstrips * rp;
+
+    // ---- row tables ----
+    std::vector<int> rowsrc_l((size_t)nrows_l * K), rowsrc_c((size_t)std::max(1, nrows_c) * K, 0);
+    std::vector<float> wy(nrows_l, 0.f);
+    std::vector<double> wyd(nrows_l, 0.0);
+    for (int i = 0; i < nrows_l; ++i) {
+        const int ii = std::min(i, dh - 1);
+        const AxisSample &s = ys[ii];
+        wy[i] = s.w;
+        wyd[i] = s.wd;
+        int t[4] = {0, 0, 0, 0};
+        if (rs == RS_NEAREST) t[0] = s.pos;
+        else if (rs == RS_BILINEAR) bilinear_taps(s.pos, 1, g.sh, t);
+        else if (rs == RS_BICUBIC) bicubic_taps(s.pos, 1, g.sh, t);
+        for (int k = 0; k < K; ++k) {
+            const int r = (rs == RS_AREA) ? s.pos + k : t[k];
+            rowsrc_l[(size_t)i * K + k] = std::max(0, std::min(g.y0 + r, H - 1));
+        }
+    }
+    if (need_uv) {
+        for (int ci = 0; ci < nrows_c; ++ci) {
+            const int cc = std::min(ci, std::max(ch2 - 1, 0));
+            const AxisSample &s = ys[std::min(cc, dh - 1)];  // luma-grid formula at the chroma index
+            int t[4] = {0, 0, 0, 0};
+            if (rs == RS_NEAREST) t[0] = s.pos;
+            else if (rs == RS_BILINEAR) bilinear_taps(s.pos, 1, g.sh / 2, t);
+            else if (rs == RS_BICUBIC) bicubic_taps(s.pos, 1, g.sh / 2, t);
+            for (int k = 0; k < K; ++k) {
+                const int r = (rs == RS_AREA) ? s.pos + k : t[k];
+                rowsrc_c[(size_t)ci * K + k] = std::max(0, std::min(g.y0 / 2 + r, H / 2 - 1));
+            }
+        }
+    }
+
+    // ---- bicubic weights, computed on the device with the reference's own pow() ----
+    std::vector<double> cxw, cyw;  // [dw][4], [nrows_l][4]
+    if (rs == RS_BICUBIC) {
+        std::vector<double> wall((size_t)dw + nrows_l);
+        for (int j = 0; j < dw; ++j) wall[j] = xs[j].wd;
+        for (int i = 0; i < nrows_l; ++i) wall[(size_t)dw + i] = wyd[i];
+        double *dW = nullptr, *dC = nullptr;
+        const int n = (int)wall.size();
+        TSVPP_CUDA(cudaMalloc(&dW, sizeof(double) * n));
+        TSVPP_CUDA(cudaMalloc(&dC, sizeof(double) * 4 * n));
+        TSVPP_CUDA(cudaMemcpy(dW, wall.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+        launch_bicubic_weights(dW, dC, n, 0);
+        std::vector<double> call((size_t)4 * n);
+        TSVPP_CUDA(cudaMemcpy(call.data(), dC, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+        cudaFree(dW);
+        cudaFree(dC);
+        cxw.assign(call.begin(), call.begin() + (size_t)4 * dw);
+        cyw.assign(call.begin() + (size_t)4 * dw, call.end());
+    }
+
+    // ---- column tables with tile-relative offsets ----
+    const int ncol = ntiles * tw;
+    DeviceArena ar;
+    size_t off_col_l = 0, off_col_c = 0;
+    auto rel = [&](int abs_pos, int a0) { return std::max(0, abs_pos - a0); };
+    if (rs == RS_NEAREST) {
+        std::vector<ColNearest> cl(ncol, ColNearest{0}), cc(ncol, ColNearest{0});
+        for (int j = 0; j < dw; ++j) {
+            const int t = j / tw;
+            cl[j].o = rel(tap_l[(size_t)j * 4], a0l[t]);
+            if (need_uv && lo_c[j] >= 0) cc[j].o = rel(tap_c[(size_t)j * 4], a0c[t]);
+        }
+        off_col_l = ar.add(cl.data(), cl.size() * sizeof(ColNearest));
+        off_col_c = ar.add(cc.data(), cc.size() * sizeof(ColNearest));
+    } else if (rs == RS_BILINEAR) {
+        std::vector<ColBilinear> cl(ncol, ColBilinear{0, 0, 0.f, 0}), cc(ncol, ColBilinear{0, 0, 0.f, 0});
+        for (int j = 0; j < dw; ++j) {
+            const int t = j / tw;
+            cl[j].o0 = rel(tap_l[(size_t)j * 4 + 0], a0l[t]);
+            cl[j].o1 = rel(tap_l[(size_t)j * 4 + 1], a0l[t]);
+            cl[j].w = xs[j].w;
+            if (need_uv && lo_c[j] >= 0) {
+                cc[j].o0 = rel(tap_c[(size_t)j * 4 + 0], a0c[t]);
+                cc[j].o1 = rel(tap_c[(size_t)j * 4 + 1], a0c[t]);
+                cc[j].w = xs[j >> 1].w;
+            }
+        }
+        off_col_l = ar.add(cl.data(), cl.size() * sizeof(ColBilinear));
+        off_col_c = ar.add(cc.data(), cc.size() * sizeof(ColBilinear));
+    } else if (rs == RS_BICUBIC) {
+        ColBicubic z;
+        std::memset(&z, 0, sizeof(z));
+        std::vector<ColBicubic> cl(ncol, z), cc(ncol, z);
+        for (int j = 0; j < dw; ++j) {
+            const int t = j / tw;
+            for (int k = 0; k < 4; ++k) {
+                cl[j].o[k] = rel(tap_l[(size_t)j * 4 + k], a0l[t]);
+                cl[j].c[k] = cxw[(size_t)4 * j + k];
+            }
+            if (need_uv && lo_c[j] >= 0) {
+                for (int k = 0; k < 4; ++k) {
+                    cc[j].o[k] = rel(tap_c[(size_t)j * 4 + k], a0c[t]);
+                    cc[j].c[k] = cxw[(size_t)4 * (j >> 1) + k];
+                }
+            }
+        }
+        off_col_l = ar.add(cl.data(), cl.size() * sizeof(ColBicubic));
+        off_col_c = ar.add(cc.data(), cc.size() * sizeof(ColBicubic));
+    } else {
+        std::vector<ColArea> cl(ncol, ColArea{0, 0}), cc(ncol, ColArea{0, 0});
+        for (int j = 0; j < dw; ++j) {
+            const int t = j / tw;
+            cl[j].o = rel(tap_l[(size_t)j * 4], a0l[t]);
+            cl[j].prow = j % PX;  // Resize.cu:198
+            if (need_uv && lo_c[j] >= 0) {
+                cc[j].o = rel(tap_c[(size_t)j * 4], a0c[t]);
+                cc[j].prow = (j >> 1) % PX;
+            }
+        }
+        off_col_l = ar.add(cl.data(), cl.size() * sizeof(ColArea));
+        off_col_c = ar.add(cc.data(), cc.size() * sizeof(ColArea));
+    }
+    const size_t off_a0l = ar.add(a0l.data(), a0l.size() * sizeof(int));
+    const size_t off_lenl = ar.add(lenl.data(), lenl.size() * sizeof(int));
+    const size_t off_a0c = ar.add(a0c.data(), a0c.size() * sizeof(int));
+    const size_t off_lenc = ar.add(lenc.data(), lenc.size() * sizeof(int));
+    const size_t off_rsl = ar.add(rowsrc_l.data(), rowsrc_l.size() * sizeof(int));
+    const size_t off_rsc = ar.add(rowsrc_c.data(), rowsrc_c.size() * sizeof(int));
+    const size_t off_wy = ar.add(wy.data(), wy.size() * sizeof(float));
+    const size_t off_cy = ar.add(cyw.data(), cyw.size() * sizeof(double));
+    const size_t off_px = ar.add(patx.data(), patx.size() * sizeof(float));
+    const size_t off_py = ar.add(paty.data(), paty.size() * sizeof(float));
+
+    TSVPP_CUDA(cudaMalloc(&pl->dev_tables, ar.host.size() + 256));
+    TSVPP_CUDA(cudaMemcpy(pl->dev_tables, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice));
+    const unsigned char *base = (const unsigned char *)pl->dev_tables;
+
+    PlanDev &D = pl->dev;
+    D.dw = dw; D.dh = dh; D.cw2 = cw2; D.ch2 = ch2;
+    D.tw = tw; D.ntiles = ntiles; D.nstrips = nstrips; D.rp = rp;
+    D.K = K; D.KX = KX;
+    D.slot_stride = slot_stride;
+    D.stage_bytes = (need_uv ? 3 : 2) * rp * K * slot_stride;
+    D.nstages = nstages;
+    D.pitch_y = pitch_y; D.pitch_uv = pitch_uv;
+    D.plane_bytes_y = plane_y; D.plane_bytes_uv = plane_uv;
+    D.swap_rb = (p.fourcc == TSVPP_BGR24) ? 1 : 0;  // ColorConversion.cu:305
+    D.need_uv = need_uv ? 1 : 0;
+    D.PX = PX; D.PY = PY;
+    D.seg_a0_l = (const int *)(base + off_a0l);
+    D.seg_len_l = (const int *)(base + off_lenl);
+    D.seg_a0_c = (const int *)(base + off_a0c);
+    D.seg_len_c = (const int *)(base + off_lenc);
+    D.rowsrc_l = (const int *)(base + off_rsl);
+    D.rowsrc_c = (const int *)(base + off_rsc);
+    D.col_l = base + off_col_l;
+    D.col_c = base + off_col_c;
+    D.wy = (const float *)(base + off_wy);
+    D.cy = (const double *)(base + off_cy);
+    D.px = (const float *)(base + off_px);
+    D.py = (const float *)(base + off_py);
+
+    pl->rs = rs;
+    pl->ok = ok;
+    pl->bulk = bulk;
+    pl->smem = fused_smem_bytes(D, bulk);
+    if (pl->smem > smem_cap) return TSVPP_UNSUPPORTED;
+    int rc = configure_fused(rs, ok, bulk, pl->smem);
+    if (rc) return rc;
+    pl->ctas_per_sm = std::max(1, max_ctas_per_sm(rs, ok, bulk, pl->smem));
+    const int cap_ctas = env_int("TSVPP_CTAS_PER_SM", 0);
+    if (cap_ctas > 0) pl->ctas_per_sm = std::min(pl->ctas_per_sm, cap_ctas);
+    pl->out_w = dw;
+    pl->out_h = dh;
+    pl->out_elems = (size_t)(channels_of(p.fourcc) * dw * dh);
+    pl->elem_size = (p.normalization || p.fourcc == TSVPP_HSV) ? 4 : 1;
+    pl->vec_ok_geom = (dw % 4 == 0) ? 1 : 0;
+    char buf[512];
+    static const char *rs_names[] = {"nearest", "bilinear", "bicubic", "area"};
+    std::snprintf(buf, sizeof(buf),
+                  "resample=%s out_kind=%d fill=%s tw=%d rp=%d K=%d KX=%d ntiles=%d nstrips=%d slot_stride=%d "
+                  "stage_bytes=%d nstages=%d smem=%zu ctas_per_sm=%d crop=%d resize=%d",
+                  rs_names[rs], ok, bulk ? "bulk" : "ldg", tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
+                  nstages, pl->smem, pl->ctas_per_sm, (int)g.crop, (int)g.resize);
+    pl->desc = buf;
+    out = std::move(pl);
+    return TSVPP_OK;
+}
+
+bool frames_bulk_ok(const TsvppFrame *f, int n) {
+    for (int i = 0; i < n; ++i) {
+        const int py = f[i].pitch_y ? f[i].pitch_y : f[i].width;
+        const int puv = f[i].pitch_uv ? f[i].pitch_uv : f[i].width;
+        if (((uintptr_t)f[i].y & 15) || ((uintptr_t)f[i].uv & 15) || (py & 15) || (puv & 15)) return false;
+    }
+    return true;
+}
+
+int get_plan(TsvppContext *ctx, const TsvppFrame &f0, const TsvppParams &p, bool bulk, Plan **out) {
+    PlanKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.w = f0.width;
+    key.h = f0.height;
+    key.pitch_y = f0.pitch_y ? f0.pitch_y : f0.width;
+    key.pitch_uv = f0.pitch_uv ? f0.pitch_uv : f0.width;
+    key.bulk = bulk ? 1 : 0;
+    key.p = p;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->plans.find(key);
+    if (it == ctx->plans.end()) {
+        std::unique_ptr<Plan> pl;
+        int rc = build_plan(ctx, key.w, key.h, key.pitch_y, key.pitch_uv, p, bulk, pl);
+        if (rc) return rc;
+        it = ctx->plans.emplace(key, std::move(pl)).first;
+    }
+    *out = it->second.get();
+    return TSVPP_OK;
+}
+
+int check_uniform(const TsvppFrame *f, int n) {
+    for (int i = 1; i < n; ++i)
+        if (f[i].width != f[0].width || f[i].height != f[0].height || f[i].pitch_y != f[0].pitch_y ||
+            f[i].pitch_uv != f[0].pitch_uv)
+            return TSVPP_UNSUPPORTED;
+    return TSVPP_OK;
+}
+
+int vec_ok_for(const Plan *pl, void *const *out, int n) {
+    if (!pl->vec_ok_geom) return 0;
+    for (int i = 0; i < n; ++i)
+        if ((uintptr_t)out[i] & 15) return 0;
+    return 1;
+}
+
+int grid_for(const TsvppContext *ctx, const Plan *pl, int n) {
+    const long items = (long)n * pl->dev.nstrips * pl->dev.ntiles;
+    const long cap = (long)ctx->sm_count * pl->ctas_per_sm;
+    return (int)std::max(1L, std::min(items, cap));
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char *tsvpp_version(void) { return "tsvpp-b200 0.1 (sm_100a)"; }
+
+int tsvpp_create(int device, TsvppContext **out) {
+    if (!out) return TSVPP_ERROR;
+    int ndev = 0;
+    TSVPP_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return (int)cudaErrorInvalidDevice;
+    TSVPP_CUDA(cudaSetDevice(device));
+    std::unique_ptr<TsvppContext> c(new TsvppContext());
+    c->device = device;
+    int v = 0;
+    TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    c->sm_count = v;
+    TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    c->smem_optin = (size_t)v;
+    *out = c.release();
+    return TSVPP_OK;
+}
+
+void tsvpp_destroy(TsvppContext *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < TsvppContext::kRing; ++i) {
+        if (ctx->ring_host[i]) cudaFreeHost(ctx->ring_host[i]);
+        if (ctx->ring_dev[i]) cudaFree(ctx->ring_dev[i]);
+        if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+        if (ctx->hstream[i]) cudaStreamDestroy(ctx->hstream[i]);
+        if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
+    }
+    ctx->plans.clear();
+    delete ctx;
+}
+
+int tsvpp_output_info(int src_width, int src_height, const TsvppParams *p, int *out_w, int *out_h, size_t *elems,
+                      int *elem_size) {
+    if (!p) return TSVPP_ERROR;
+    const Geometry g = resolve_geometry(src_width, src_height, *p);
+    if (out_w) *out_w = g.dw;
+    if (out_h) *out_h = g.dh;
+    if (elems) *elems = (size_t)(channels_of(p->fourcc) * g.dw * g.dh);
+    if (elem_size) *elem_size = (p->normalization || p->fourcc == TSVPP_HSV) ? 4 : 1;
+    return TSVPP_OK;
+}
+
+int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
+                        void *stream_) {
+    if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_uniform(frames, n);
+    if (rc) return rc;
+    const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
+    Plan *pl = nullptr;
+    rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+    if (rc) return rc;
+
+    // descriptor upload through a small ring of pinned buffers (stream-ordered, no host sync
+    // unless all ring slots are still in flight)
+    int slot;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        slot = ctx->ring_next;
+        ctx->ring_next = (ctx->ring_next + 1) % TsvppContext::kRing;
+        if (ctx->ring_ev[slot]) TSVPP_CUDA(cudaEventSynchronize(ctx->ring_ev[slot]));
+        else TSVPP_CUDA(cudaEventCreateWithFlags(&ctx->ring_ev[slot], cudaEventDisableTiming));
+        if (ctx->ring_cap[slot] < n) {
+            if (ctx->ring_host[slot]) cudaFreeHost(ctx->ring_host[slot]);
+            if (ctx->ring_dev[slot]) cudaFree(ctx->ring_dev[slot]);
+            const int cap = std::max(n, 64);
+            TSVPP_CUDA(cudaMallocHost(&ctx->ring_host[slot], sizeof(FrameDev) * cap));
+            TSVPP_CUDA(cudaMalloc(&ctx->ring_dev[slot], sizeof(FrameDev) * cap));
+            ctx->ring_cap[slot] = cap;
+        }
+    }
+    FrameDev *h = ctx->ring_host[slot];
+    for (int i = 0; i < n; ++i) {
+        h[i].y = frames[i].y;
+        h[i].uv = frames[i].uv;
+        h[i].out = out[i];
+    }
+    TSVPP_CUDA(cudaMemcpyAsync(ctx->ring_dev[slot], h, sizeof(FrameDev) * n, cudaMemcpyHostToDevice, stream));
+    rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n),
+                      grid_for(ctx, pl, n), pl->smem, stream);
+    TSVPP_CUDA(cudaEventRecord(ctx->ring_ev[slot], stream));
+    ctx->launches.fetch_add(1);
+    return rc;
+}
+
+int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
+                       TsvppBatch **batch) {
+    if (!ctx || !frames || !p || !out || !batch || n <= 0) return TSVPP_ERROR;
+    int rc = check_uniform(frames, n);
+    if (rc) return rc;
+    const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
+    Plan *pl = nullptr;
+    rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+    if (rc) return rc;
+    std::unique_ptr<TsvppBatch> b(new TsvppBatch());
+    b->ctx = ctx;
+    b->plan = pl;
+    b->n = n;
+    b->vec_ok = vec_ok_for(pl, out, n);
+    b->grid = grid_for(ctx, pl, n);
+    std::vector<FrameDev> h(n);
+    for (int i = 0; i < n; ++i) {
+        h[i].y = frames[i].y;
+        h[i].uv = frames[i].uv;
+        h[i].out = out[i];
+    }
+    TSVPP_CUDA(cudaMalloc(&b->frames_dev, sizeof(FrameDev) * n));
+    TSVPP_CUDA(cudaMemcpy(b->frames_dev, h.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice));
+    *batch = b.release();
+    return TSVPP_OK;
+}
+
+int tsvpp_batch_run(TsvppBatch *b, void *stream) {
+    if (!b) return TSVPP_ERROR;
+    const Plan *pl = b->plan;
+    int rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, b->frames_dev, b->n, b->vec_ok, b->grid, pl->smem,
+                          (cudaStream_t)stream);
+    b->ctx->launches.fetch_add(1);
+    return rc;
+}
+
+void tsvpp_batch_destroy(TsvppBatch *b) {
+    if (!b) return;
+    if (b->frames_dev) cudaFree(b->frames_dev);
+    delete b;
+}
+
+int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                             void *const *out) {
+    if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
+    int rc = check_uniform(frames, n);
+    if (rc) return rc;
+    TSVPP_CUDA(cudaSetDevice(ctx->device));
+    const int W = frames[0].width, H = frames[0].height;
+    const int py = frames[0].pitch_y ? frames[0].pitch_y : W, puv = frames[0].pitch_uv ? frames[0].pitch_uv : W;
+    size_t elems = 0;
+    int es = 1, ow = 0, oh = 0;
+    tsvpp_output_info(W, H, p, &ow, &oh, &elems, &es);
+    const size_t in_y = (size_t)py * H, in_uv = (size_t)puv * (H / 2);
+    const size_t in_y_pad = (in_y + 255) / 256 * 256, in_uv_pad = (in_uv + 255) / 256 * 256;
+    const size_t in_frame = in_y_pad + in_uv_pad;
+    const size_t out_frame = (elems * es + 255) / 256 * 256;
+    // chunks of frames ping-pong over two streams so that H2D, kernel and D2H overlap
+    const int chunk = std::max(1, std::min(n, env_int("TSVPP_HOST_CHUNK", 16)));
+    for (int s = 0; s < 2; ++s) {
+        if (!ctx->hstream[s]) TSVPP_CUDA(cudaStreamCreateWithFlags(&ctx->hstream[s], cudaStreamNonBlocking));
+        if (!ctx->hev[s]) TSVPP_CUDA(cudaEventCreateWithFlags(&ctx->hev[s], cudaEventDisableTiming));
+        if (ctx->stage_in_cap[s] < in_frame * chunk) {
+            if (ctx->stage_in[s]) cudaFree(ctx->stage_in[s]);
+            TSVPP_CUDA(cudaMalloc(&ctx->stage_in[s], in_frame * chunk));
+            ctx->stage_in_cap[s] = in_frame * chunk;
+        }
+        if (ctx->stage_out_cap[s] < out_frame * chunk) {
+            if (ctx->stage_out[s]) cudaFree(ctx->stage_out[s]);
+            TSVPP_CUDA(cudaMalloc(&ctx->stage_out[s], out_frame * chunk));
+            ctx->stage_out_cap[s] = out_frame * chunk;
+        }
+    }
+    std::vector<TsvppFrame> dframes(chunk);
+    std::vector<void *> douts(chunk);
+    int which = 0;
+    for (int base = 0; base < n; base += chunk, which ^= 1) {
+        const int m = std::min(chunk, n - base);
+        cudaStream_t st = ctx->hstream[which];
+        for (int k = 0; k < m; ++k) {
+            unsigned char *dy = ctx->stage_in[which] + in_frame * k;
+            unsigned char *duv = dy + in_y_pad;
+            TSVPP_CUDA(cudaMemcpyAsync(dy, frames[base + k].y, in_y, cudaMemcpyHostToDevice, st));
+            TSVPP_CUDA(cudaMemcpyAsync(duv, frames[base + k].uv, in_uv, cudaMemcpyHostToDevice, st));
+            dframes[k] = frames[base + k];
+            dframes[k].y = dy;
+            dframes[k].uv = duv;
+            douts[k] = ctx->stage_out[which] + out_frame * k;
+        }
+        rc = tsvpp_convert_batch(ctx, dframes.data(), m, p, douts.data(), st);
+        if (rc) return rc;
+        for (int k = 0; k < m; ++k)
+            TSVPP_CUDA(cudaMemcpyAsync(out[base + k], douts[k], elems * es, cudaMemcpyDeviceToHost, st));
+        // the staging buffers of this stream are reused two chunks later: the stream order
+        // already serialises that, nothing to wait for on the host here
+    }
+    TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
+    TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[1]));
+    return TSVPP_OK;
+}
+
+unsigned long long tsvpp_launch_count(const TsvppContext *ctx) { return ctx ? ctx->launches.load() : 0ull; }
+
+int tsvpp_describe_plan(TsvppContext *ctx, const TsvppFrame *f0, const TsvppParams *p, char *buf, size_t buflen) {
+    if (!ctx || !f0 || !p || !buf || !buflen) return TSVPP_ERROR;
+    Plan *pl = nullptr;
+    const bool bulk = frames_bulk_ok(f0, 1) && !env_int("TSVPP_FORCE_LDG", 0);
+    int rc = get_plan(ctx, *f0, *p, bulk, &pl);
+    if (rc) return rc;
+    std::snprintf(buf, buflen, "%s", pl->desc.c_str());
+    return TSVPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+// vpp_launch.h -- host-callable entry points of vpp_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "vpp_plan.h"
+
+namespace tsvpp {
+
+size_t fused_smem_bytes(const PlanDev &P, bool bulk);
+int configure_fused(int rs, int ok, bool bulk, size_t smem_bytes);
+int max_ctas_per_sm(int rs, int ok, bool bulk, size_t smem_bytes);
+int launch_fused(int rs, int ok, bool bulk, const PlanDev &P, const FrameDev *frames_dev, int nframes, int vec_ok,
+                 int grid, size_t smem_bytes, cudaStream_t stream);
+void launch_bicubic_weights(const double *w_dev, double *c_dev, int n, cudaStream_t stream);
+
+}  // namespace tsvpp
