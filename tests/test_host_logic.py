@@ -1,0 +1,165 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/tsvpp.h declares,
+the host dispatch rules equal the oracle's, helper arithmetic used by the kernels is exact, and
+the multi-rank layout (world_size 2, gloo) behaves.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tensor_stream_b200 import build as B
+    from tensor_stream_b200 import vpp
+    B.build()
+    return vpp.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "tsvpp.h")).read()
+    names = set(re.findall(r"\b(tsvpp_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 11
+    for n in sorted(names):
+        assert hasattr(lib, n), "libtsvpp.so does not export %s" % n
+    assert b"sm_100a" in lib.tsvpp_version()
+
+
+def test_enum_numbering_is_the_references():
+    from tensor_stream_b200 import vpp
+    # reference include/VideoProcessor.h:20-28,32-35,59-64
+    assert [f.value for f in vpp.FourCC] == [0, 1, 2, 3, 4, 5, 6]
+    assert [f.name for f in vpp.FourCC] == ["Y800", "RGB24", "BGR24", "NV12", "UYVY", "YUV444", "HSV"]
+    assert vpp.Planes.PLANAR.value == 0 and vpp.Planes.MERGED.value == 1
+    assert [r.name for r in vpp.ResizeType] == ["NEAREST", "BILINEAR", "BICUBIC", "AREA"]
+
+
+def test_frame_parameters_defaults_match_reference():
+    from tensor_stream_b200 import vpp
+    fp = vpp.FrameParameters()
+    # ColorOptions(): RGB24, MERGED, normalization=false; ResizeOptions(): NEAREST (include/VideoProcessor.h:38-78)
+    assert (fp.pixel_format, fp.planes_pos, fp.normalization, fp.resize_type) == \
+        (vpp.FourCC.RGB24, vpp.Planes.MERGED, False, vpp.ResizeType.NEAREST)
+    assert vpp.FrameParameters(pixel_format=vpp.FourCC.HSV).normalization is True  # HSV ctor rule (:45-46)
+
+
+@pytest.mark.parametrize("crop,dst,exp", [
+    ((0, 0, 0, 0), (0, 0), (1080, 608)),
+    ((0, 0, 320, 240), (0, 0), (320, 240)),
+    ((0, 0, 1080, 608), (0, 0), (1080, 608)),      # crop == frame: ignored (strictly smaller rule)
+    ((0, 0, 1080, 300), (0, 0), (1080, 608)),      # one side not smaller: ignored
+    ((0, 0, 320, 240), (720, 480), (720, 480)),
+    ((0, 0, 0, 0), (540, 304), (540, 304)),
+    ((10, 10, 5, 5), (0, 0), (1080, 608)),          # negative area: ignored
+])
+def test_output_info_follows_reference_dispatch(lib, crop, dst, exp):
+    from oracle import oracle as O
+    from tensor_stream_b200 import vpp
+    for fourcc, ch in ((vpp.FourCC.RGB24, 3), (vpp.FourCC.Y800, 1), (vpp.FourCC.NV12, 1.5), (vpp.FourCC.UYVY, 2)):
+        fp = vpp.FrameParameters(dst[0], dst[1], crop_coords=crop, pixel_format=fourcc)
+        w, h, n, es = vpp.output_info(1080, 608, fp)
+        assert (w, h) == exp == O.out_geometry(1080, 608, crop, dst)
+        assert n == int(ch * w * h) and es == 1
+    fp = vpp.FrameParameters(dst[0], dst[1], crop_coords=crop, pixel_format=vpp.FourCC.HSV)
+    assert vpp.output_info(1080, 608, fp)[3] == 4
+
+
+def test_output_shapes_match_reference_from_blob():
+    from tensor_stream_b200 import vpp
+    # src/Wrappers/WrapperPython.cpp:318-341
+    mk = lambda **k: vpp.FrameParameters(256, 128, **k)
+    assert vpp.output_shape(1920, 1080, mk())[0] == (128, 256, 3)
+    assert vpp.output_shape(1920, 1080, mk(planes_pos=vpp.Planes.PLANAR))[0] == (3, 128, 256)
+    assert vpp.output_shape(1920, 1080, mk(pixel_format=vpp.FourCC.Y800))[0] == (1, 128, 256)
+    assert vpp.output_shape(1920, 1080, mk(pixel_format=vpp.FourCC.NV12))[0] == (1, 192, 256)
+    assert vpp.output_shape(1920, 1080, mk(pixel_format=vpp.FourCC.UYVY))[0] == (1, 256, 256)
+    assert vpp.output_shape(1920, 1080, mk(pixel_format=vpp.FourCC.HSV)) == ((128, 256, 3), 4)
+
+
+def test_div255_reciprocal_trick_is_exact():
+    """csrc/vpp_kernels.cu div255(): q=x*r; e=fma(-q,255,x); q+=e*r must equal IEEE x/255.f for
+    all 256 inputs (the reference divides, ColorConversion.cu:50)."""
+    src = r'''
+#include <math.h>
+#include <stdio.h>
+int main(){ const float r = 0x1.010102p-8f; int bad = 0;
+ for (int c = 0; c < 256; c++) { float x = (float)c, q = x * r, e = fmaf(-q, 255.0f, x), v = fmaf(e, r, q);
+   if (v != x / 255.0f) bad++; }
+ printf("%d\n", bad); return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", os.path.join(d, "t"),
+                               os.path.join(d, "t.c"), "-lm"])
+        assert subprocess.check_output([os.path.join(d, "t")]).strip() == b"0"
+
+
+def test_area_pattern_examples():
+    """generateResizePattern (reference src/Resize.cu:359-386) on the examples of SURVEY.md A.5."""
+    from oracle import oracle as O
+    np.testing.assert_array_equal(O.area_pattern(1.5), np.array([[1, .5], [.5, 1]], dtype=np.float32))
+    assert O.area_pattern(7.5).shape == (2, 8)
+    assert O.area_pattern(1080 / 256).shape == (32, 5)
+    assert O.area_pattern(2.0).shape == (1, 2)
+    p = O.area_pattern(np.float32(1920) / np.float32(299))
+    assert p.shape == (299, 7)  # period = dst/gcd(src,dst); rows may drop a surplus tail weight
+
+
+def test_oracle_edge_cases_do_not_read_out_of_bounds():
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    y = rng.integers(0, 256, (64, 96), dtype=np.uint8)
+    uv = rng.integers(0, 256, (32, 96), dtype=np.uint8)
+    for rt in (O.NEAREST, O.BILINEAR, O.BICUBIC, O.AREA):
+        for dst in ((48, 32), (192, 128), (96, 64), (32, 100)):
+            out, (w, h), oob = O.convert(y, uv, dst=dst, resize_type=rt, return_oob=True)
+            assert (w, h) == dst and out.size == 3 * w * h and oob == 0, (rt, dst, oob)
+
+
+def test_stream_sharding_is_a_partition():
+    from tensor_stream_b200 import sharding as S
+    for world in (1, 2, 4, 8):
+        owned = [S.streams_of_rank(19, world, r) for r in range(world)]
+        assert sorted(sum(owned, [])) == list(range(19))
+        assert all(S.rank_of_stream(s, world) == r for r, ss in enumerate(owned) for s in ss)
+    assert S.aggregate_fps(192, 20, 10.0, 8) == 8 * 192 * 20 / 0.010
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tensor_stream_b200 import sharding as S
+    mine = S.streams_of_rank(8, world, rank)
+    ms = [10.0 + 5.0 * rank, 100.0 - rank]
+    q.put((rank, mine, S.max_over_ranks(ms)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_layout_over_gloo():
+    """world_size 2 on CPU: each rank owns a disjoint half of the streams and the timing
+    reduction returns the max over ranks on every rank (what bench.py --gpus N relies on)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5, 7]
+    assert res[0][2] == res[1][2] == [15.0, 100.0]
