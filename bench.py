@@ -152,15 +152,14 @@ def cpu_baseline(threads=None, seconds=12.0):
               for _ in range(4)]
     kw = dict(dst=(DW, DH), resize_type=O.BILINEAR, fourcc=O.BGR24, planes=O.PLANAR, normalization=True)
     O.convert(*frames[0], **kw)  # warm
-    t0 = time.perf_counter()
-    O.convert(*frames[0], **kw)
-    per = max(time.perf_counter() - t0, 1e-5)
-    per_thread = max(8, int(seconds / per))
+    deadline = time.perf_counter() + seconds
 
     def work(tid):
-        for k in range(per_thread):
+        k = 0
+        while time.perf_counter() < deadline:
             O.convert(*frames[(tid + k) % len(frames)], **kw)
-        return per_thread
+            k += 1
+        return k
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
@@ -187,25 +186,24 @@ def swscale_baseline(cores, seconds=6.0):
     y = rng.integers(0, 256, (H, W), dtype=np.uint8)
     uv = rng.integers(0, 256, (H // 2, W), dtype=np.uint8)
 
-    def work(n):
+    def work(deadline):
         ctx = sws.sws_getContext(W, H, 23, DW, DH, 3, 2, None, None, None)  # NV12=23, BGR24=3, SWS_BILINEAR=2
         dst = np.empty((DH, DW, 3), dtype=np.uint8)
         src = (C.c_void_p * 4)(y.ctypes.data, uv.ctypes.data, None, None)
         sst = (C.c_int * 4)(W, W, 0, 0)
         dp = (C.c_void_p * 4)(dst.ctypes.data, None, None, None)
         dst_st = (C.c_int * 4)(DW * 3, 0, 0, 0)
-        for _ in range(n):
+        n = 0
+        while time.perf_counter() < deadline[0]:
             sws.sws_scale(ctx, src, sst, 0, H, dp, dst_st)
+            n += 1
         sws.sws_freeContext(ctx)
         return n
 
-    t0 = time.perf_counter()
-    work(20)
-    per = (time.perf_counter() - t0) / 20
-    n = max(20, int(seconds / per))
+    deadline = [time.perf_counter() + seconds]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
-        done = sum(ex.map(work, [n] * cores))
+        done = sum(ex.map(work, [deadline] * cores))
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "frames/sec", "cores": cores,
             "what": "FFmpeg 8 libswscale NV12->BGR24 256x256 SWS_BILINEAR uint8"}
@@ -249,6 +247,15 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # The timed region is K launches of ~0.1 ms: far below nvidia-smi's 200 ms sampling period.
+    # Bracket it with an untimed soak of the SAME launches so that (a) the clocks line is sampled
+    # under this very load and (b) the timed steps run at sustained, not burst, clocks.
+    soak_s = float(os.environ.get("BENCH_SOAK_S", "1.0"))
+    t_end = time.perf_counter() + soak_s
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            batch.run(stream)
+        torch.cuda.synchronize()
     l0 = v.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -260,6 +267,11 @@ def run_ours(args):
     launches = v.launch_count() - l0
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    t_end = time.perf_counter() + 0.5 * soak_s
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            batch.run(stream)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: host buffers through the C ABI (H2D + kernel + D2H inside the call) ----
@@ -368,6 +380,18 @@ def run_reference(args):
                 th.join()
         ref.sync()
 
+    # give the reference its best host-thread count ("all the host threads it can use"): its
+    # per-frame cudaMalloc/cudaFree serialise device-wide, so more consumers can be slower
+    best = None
+    for cand in (1, 2, min(4, os.cpu_count() or 1)):
+        nthreads = cand
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, cand)
+    nthreads = best[1]
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local)

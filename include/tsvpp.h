@@ -105,7 +105,13 @@ unsigned long long tsvpp_launch_count(const TsvppContext *ctx);
  * smem bytes, fill mode ("bulk" = cp.async.bulk/TMA, "ldg" = fallback for unaligned frames). */
 int tsvpp_describe_plan(TsvppContext *ctx, const TsvppFrame *frame0, const TsvppParams *p, char *buf, size_t buflen);
 
+/* Test hook: pow(w,2) and pow(w,3) as evaluated by the device's libdevice (the bicubic weights of
+ * reference src/Resize.cu:45-48 depend on it bit for bit; the CPU oracle is pinned to these). */
+int tsvpp_debug_pow23(const double *w, int n, double *w2, double *w3);
+
 const char *tsvpp_version(void);
+/* Text of the last failure on the calling thread (which runtime call, where). */
+const char *tsvpp_last_error(void);
 
 #ifdef __cplusplus
 }

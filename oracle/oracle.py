@@ -50,6 +50,11 @@ def lib():
         L.vpo_area_pattern.argtypes = [C.c_float, C.c_void_p, C.c_int]
         L.vpo_area_pattern.restype = C.c_int
         L.vpo_oob_reads.restype = C.c_long
+        L.vpo_pow_table_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.vpo_pow_table_set.restype = C.c_int
+        L.vpo_pow_record.argtypes = [C.c_int]
+        L.vpo_pow_recorded.argtypes = [C.c_void_p, C.c_int]
+        L.vpo_pow_recorded.restype = C.c_int
         L.vpo_av_crc32.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
         L.vpo_av_crc32.restype = C.c_uint32
         _LIB = L
@@ -137,3 +142,27 @@ def area_pattern(scale, max_rows=8192):
     if n <= 0:
         raise RuntimeError("pattern generation failed: %d" % n)
     return buf[:n].copy()
+
+
+def pow_record(on):
+    lib().vpo_pow_record(1 if on else 0)
+
+
+def pow_recorded():
+    """Distinct-ish list of the w arguments bicubic asked pow() for since pow_record(True)."""
+    buf = np.zeros(16384, dtype=np.float64)
+    n = lib().vpo_pow_recorded(buf.ctypes.data, buf.size)
+    return np.unique(buf[:min(n, buf.size)])
+
+
+def pow_table_set(w, w2, w3):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    w2 = np.ascontiguousarray(w2, dtype=np.float64)
+    w3 = np.ascontiguousarray(w3, dtype=np.float64)
+    rc = lib().vpo_pow_table_set(w.ctypes.data, w2.ctypes.data, w3.ctypes.data, int(w.size))
+    if rc:
+        raise RuntimeError("pow table overflow")
+
+
+def pow_table_clear():
+    lib().vpo_pow_table_clear()

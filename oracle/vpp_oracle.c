@@ -62,7 +62,9 @@ static int nv12_alloc(nv12_t *im, int w, int h) {
     im->w = w;
     im->h = h;
     im->y = (uint8_t *)calloc((size_t)w * h + 64, 1);
-    im->uv = (uint8_t *)calloc((size_t)w * (h / 2) + 64, 1);
+    /* two extra zeroed chroma rows: for odd w/h the reference's colour conversion indexes one
+     * row/byte past the chroma plane (undefined there); defined as 0 here */
+    im->uv = (uint8_t *)calloc((size_t)w * (h / 2 + 2) + 64, 1);
     return (im->y && im->uv) ? 0 : -1;
 }
 static void nv12_free(nv12_t *im) {
@@ -196,9 +198,80 @@ static void resize_area_up(const plane_t *Y, const plane_t *UV, int sw, int sh, 
 static int g_bicubic_fma = 1;
 void vpo_set_bicubic_fma(int on) { g_bicubic_fma = on; }
 
+/* pow() is the one primitive of the path whose result is implementation-defined: the compiled
+ * reference calls CUDA libdevice's pow (Resize.cu:45-48), which is NOT correctly rounded, and
+ * with dyadic weights (ratios like 1.5, 2) sums land exactly on .5 ties, so a 1-ulp difference
+ * in pow(w,3) flips pixels.  CPU-only runs use libm's pow.  GPU tests pin the oracle to the
+ * device's values: record the distinct w arguments (vpo_pow_record), evaluate pow(w,2), pow(w,3)
+ * on the GPU (tsvpp_debug_pow23), install them (vpo_pow_table_set); everything else of the
+ * bicubic arithmetic is still evaluated here. */
+#define POW_TAB_CAP 16384
+static double g_pw[POW_TAB_CAP], g_pw2[POW_TAB_CAP], g_pw3[POW_TAB_CAP];
+static int g_pow_n = 0;       /* installed entries (open addressing, cap POW_TAB_CAP) */
+static uint8_t g_pow_used[POW_TAB_CAP];
+static int g_pow_record = 0;
+static double g_rec[POW_TAB_CAP];
+static int g_rec_n = 0;
+
+static inline uint32_t pow_hash(double w) {
+    uint64_t b;
+    memcpy(&b, &w, 8);
+    b ^= b >> 29;
+    b *= 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(b >> 40) & (POW_TAB_CAP - 1);
+}
+void vpo_pow_table_clear(void) {
+    memset(g_pow_used, 0, sizeof(g_pow_used));
+    g_pow_n = 0;
+}
+int vpo_pow_table_set(const double *w, const double *w2, const double *w3, int n) {
+    vpo_pow_table_clear();
+    for (int i = 0; i < n; i++) {
+        if (g_pow_n >= POW_TAB_CAP / 2) return -1;
+        uint32_t h = pow_hash(w[i]);
+        while (g_pow_used[h] && g_pw[h] != w[i]) h = (h + 1) & (POW_TAB_CAP - 1);
+        if (!g_pow_used[h]) g_pow_n++;
+        g_pow_used[h] = 1;
+        g_pw[h] = w[i];
+        g_pw2[h] = w2[i];
+        g_pw3[h] = w3[i];
+    }
+    return 0;
+}
+void vpo_pow_record(int on) {
+    g_pow_record = on;
+    if (on) g_rec_n = 0;
+}
+int vpo_pow_recorded(double *out, int cap) {
+    int n = g_rec_n < cap ? g_rec_n : cap;
+    memcpy(out, g_rec, sizeof(double) * (size_t)n);
+    return g_rec_n;
+}
+static void pow23(double w, double *w2, double *w3) {
+    if (g_pow_record) {
+        int seen = 0;
+        for (int i = g_rec_n - 1; i >= 0 && i >= g_rec_n - 8; i--) seen |= (g_rec[i] == w);
+        if (!seen && g_rec_n < POW_TAB_CAP) g_rec[g_rec_n++] = w;
+    }
+    if (g_pow_n) {
+        uint32_t h = pow_hash(w);
+        while (g_pow_used[h]) {
+            if (g_pw[h] == w) {
+                *w2 = g_pw2[h];
+                *w3 = g_pw3[h];
+                return;
+            }
+            h = (h + 1) & (POW_TAB_CAP - 1);
+        }
+    }
+    *w2 = pow(w, 2);
+    *w3 = pow(w, 3);
+}
+
 void vpo_bicubic_weights(double w, double c[4]) {
     const double a = -0.75;
-    double w2 = pow(w, 2), w3 = pow(w, 3);
+    double w2, w3;
+    pow23(w, &w2, &w3);
     if (g_bicubic_fma) {
         /* as compiled for sm_100a (cuobjdump -sass of the unmodified reference, a folded to
          * -0.75): t=w2*1.5; q=w3*-0.75; c0=fma(w,-.75,t)+q; c1=fma(w3,1.25,fma(w2,-2.25,1));

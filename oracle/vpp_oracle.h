@@ -31,6 +31,11 @@ void vpo_yuv_to_rgb(int Y, int U, int V, int *rgb);
 void vpo_rgb_to_hsv(float R, float G, float B, float *hsv);
 void vpo_bicubic_weights(double w, double c[4]);
 void vpo_set_bicubic_fma(int on);
+/* pin pow(w,2)/pow(w,3) to externally computed values (see vpp_oracle.c) */
+void vpo_pow_table_clear(void);
+int vpo_pow_table_set(const double *w, const double *w2, const double *w3, int n);
+void vpo_pow_record(int on);
+int vpo_pow_recorded(double *out, int cap);
 int vpo_area_pattern(float scale, float *out, int max_rows);
 long vpo_oob_reads(void);
 void vpo_reset_oob(void);

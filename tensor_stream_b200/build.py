@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtsvpp.so")
 
-SOURCES = ["vpp_kernels.cu", "tsvpp_capi.cpp", "VideoProcessor.cpp"]
+SOURCES = ["vpp_kernels.cu", "vpp_yuv_kernels.cu", "tsvpp_capi.cpp", "VideoProcessor.cpp"]
 HEADERS = ["vpp_plan.h", "vpp_launch.h", "../../include/tsvpp.h", "../../include/VideoProcessor.h",
            "../../include/tsvpp_avframe.h"]
 

@@ -29,10 +29,18 @@ using namespace tsvpp;
 
 namespace {
 
-#define TSVPP_CUDA(expr)                                  \
-    do {                                                  \
-        cudaError_t e_ = (expr);                          \
-        if (e_ != cudaSuccess) return (int)e_;            \
+thread_local char g_last_error[256] = "";
+
+inline int note_error(int code, const char *what, int line) {
+    std::snprintf(g_last_error, sizeof(g_last_error), "%s -> %d (%s) at tsvpp_capi.cpp:%d", what, code,
+                  code > 0 ? cudaGetErrorString((cudaError_t)code) : "tsvpp status", line);
+    return code;
+}
+
+#define TSVPP_CUDA(expr)                                              \
+    do {                                                              \
+        cudaError_t e_ = (expr);                                      \
+        if (e_ != cudaSuccess) return note_error((int)e_, #expr, __LINE__); \
     } while (0)
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -688,6 +696,8 @@ extern "C" {
 
 const char *tsvpp_version(void) { return "tsvpp-b200 0.1 (sm_100a)"; }
 
+const char *tsvpp_last_error(void) { return g_last_error; }
+
 int tsvpp_create(int device, TsvppContext **out) {
     if (!out) return TSVPP_ERROR;
     int ndev = 0;
@@ -735,19 +745,9 @@ int tsvpp_output_info(int src_width, int src_height, const TsvppParams *p, int *
     return TSVPP_OK;
 }
 
-int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
-                        void *stream_) {
-    if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    int rc = check_uniform(frames, n);
-    if (rc) return rc;
-    const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
-    Plan *pl = nullptr;
-    rc = get_plan(ctx, frames[0], *p, bulk, &pl);
-    if (rc) return rc;
-
-    // descriptor upload through a small ring of pinned buffers (stream-ordered, no host sync
-    // unless all ring slots are still in flight)
+// Descriptor upload through a small ring of pinned buffers: stream-ordered, no host sync unless
+// all ring slots are still in flight.
+static int upload_descriptors(TsvppContext *ctx, const FrameDev *src, int n, cudaStream_t stream, int *slot_out) {
     int slot;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -758,23 +758,109 @@ int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, cons
         if (ctx->ring_cap[slot] < n) {
             if (ctx->ring_host[slot]) cudaFreeHost(ctx->ring_host[slot]);
             if (ctx->ring_dev[slot]) cudaFree(ctx->ring_dev[slot]);
+            ctx->ring_host[slot] = nullptr;
+            ctx->ring_dev[slot] = nullptr;
+            ctx->ring_cap[slot] = 0;
             const int cap = std::max(n, 64);
             TSVPP_CUDA(cudaMallocHost(&ctx->ring_host[slot], sizeof(FrameDev) * cap));
             TSVPP_CUDA(cudaMalloc(&ctx->ring_dev[slot], sizeof(FrameDev) * cap));
             ctx->ring_cap[slot] = cap;
         }
     }
-    FrameDev *h = ctx->ring_host[slot];
+    std::memcpy(ctx->ring_host[slot], src, sizeof(FrameDev) * n);
+    TSVPP_CUDA(cudaMemcpyAsync(ctx->ring_dev[slot], ctx->ring_host[slot], sizeof(FrameDev) * n, cudaMemcpyHostToDevice,
+                               stream));
+    *slot_out = slot;
+    return TSVPP_OK;
+}
+
+// UYVY / YUV444: (fused crop+resize -> tight NV12 u8, only when needed) + one packing kernel
+// (reference src/ColorConversion.cu:336-352)
+static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                              void *const *out, cudaStream_t stream) {
+    const int W = frames[0].width, H = frames[0].height;
+    const Geometry g = resolve_geometry(W, H, *p);
+    const int is_float = p->normalization ? 1 : 0;
+    std::vector<FrameDev> h(n);
+    unsigned char *tmp = nullptr;
+    int w = g.dw, hgt = g.dh, pitch;
+    long y_bytes, uv_bytes;
+    if (g.crop || g.resize) {
+        TsvppParams p1 = *p;
+        p1.fourcc = TSVPP_NV12;
+        p1.normalization = 0;
+        const size_t ybytes = (size_t)w * hgt;
+        const size_t fbytes = (ybytes + (size_t)w * (hgt / 2) + 255) / 256 * 256 + 256;
+        TSVPP_CUDA(cudaMallocAsync(&tmp, fbytes * n, stream));
+        // chroma rows that do not exist for odd sizes must read as 0, like the oracle's
+        TSVPP_CUDA(cudaMemsetAsync(tmp, 0, fbytes * n, stream));
+        std::vector<void *> o1(n);
+        for (int i = 0; i < n; ++i) o1[i] = tmp + fbytes * i;
+        int rc = tsvpp_convert_batch(ctx, frames, n, &p1, o1.data(), stream);
+        if (rc) {
+            cudaFreeAsync(tmp, stream);
+            return rc;
+        }
+        for (int i = 0; i < n; ++i) {
+            h[i].y = tmp + fbytes * i;
+            h[i].uv = tmp + fbytes * i + ybytes;
+            h[i].out = out[i];
+        }
+        pitch = w;
+        y_bytes = (long)ybytes;
+        uv_bytes = (long)(fbytes - ybytes);
+    } else {
+        // straight from the input frame; BOTH planes indexed with linesize[0] (ColorConversion.cu:301)
+        pitch = frames[0].pitch_y ? frames[0].pitch_y : W;
+        const int puv = frames[0].pitch_uv ? frames[0].pitch_uv : W;
+        y_bytes = (long)pitch * H;
+        uv_bytes = (long)puv * (H / 2);
+        for (int i = 0; i < n; ++i) {
+            h[i].y = frames[i].y;
+            h[i].uv = frames[i].uv;
+            h[i].out = out[i];
+        }
+    }
+    int slot = 0;
+    int rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
+    if (rc == TSVPP_OK) {
+        (void)cudaGetLastError();
+        rc = launch_packed_yuv(p->fourcc == TSVPP_YUV444, is_float, ctx->ring_dev[slot], n, w, hgt, pitch, y_bytes,
+                               uv_bytes, is_float, stream);
+        cudaEventRecord(ctx->ring_ev[slot], stream);
+        ctx->launches.fetch_add(1);
+        if (rc) note_error(rc, "launch_packed_yuv", __LINE__);
+    }
+    if (tmp) cudaFreeAsync(tmp, stream);
+    return rc;
+}
+
+int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
+                        void *stream_) {
+    if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_uniform(frames, n);
+    if (rc) return rc;
+    if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444) return convert_packed_yuv(ctx, frames, n, p, out, stream);
+    const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
+    Plan *pl = nullptr;
+    rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+    if (rc) return rc;
+    std::vector<FrameDev> h(n);
     for (int i = 0; i < n; ++i) {
         h[i].y = frames[i].y;
         h[i].uv = frames[i].uv;
         h[i].out = out[i];
     }
-    TSVPP_CUDA(cudaMemcpyAsync(ctx->ring_dev[slot], h, sizeof(FrameDev) * n, cudaMemcpyHostToDevice, stream));
+    int slot = 0;
+    rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
+    if (rc) return rc;
+    (void)cudaGetLastError();  // drop stale non-sticky errors of unrelated earlier calls
     rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n),
                       grid_for(ctx, pl, n), pl->smem, stream);
     TSVPP_CUDA(cudaEventRecord(ctx->ring_ev[slot], stream));
     ctx->launches.fetch_add(1);
+    if (rc) return note_error(rc, "launch_fused", __LINE__);
     return rc;
 }
 
@@ -808,9 +894,11 @@ int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const
 int tsvpp_batch_run(TsvppBatch *b, void *stream) {
     if (!b) return TSVPP_ERROR;
     const Plan *pl = b->plan;
+    (void)cudaGetLastError();
     int rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, b->frames_dev, b->n, b->vec_ok, b->grid, pl->smem,
                           (cudaStream_t)stream);
     b->ctx->launches.fetch_add(1);
+    if (rc) return note_error(rc, "launch_fused", __LINE__);
     return rc;
 }
 
@@ -876,6 +964,18 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
     }
     TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
     TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[1]));
+    return TSVPP_OK;
+}
+
+int tsvpp_debug_pow23(const double *w, int n, double *w2, double *w3) {
+    if (!w || !w2 || !w3 || n <= 0) return TSVPP_ERROR;
+    double *d = nullptr;
+    TSVPP_CUDA(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+    TSVPP_CUDA(cudaMemcpy(d, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+    launch_pow23(d, d + n, d + 2 * (size_t)n, n, 0);
+    TSVPP_CUDA(cudaMemcpy(w2, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    TSVPP_CUDA(cudaMemcpy(w3, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return TSVPP_OK;
 }
 

@@ -559,6 +559,18 @@ __global__ void bicubic_weights_kernel(const double *__restrict__ w, double *__r
     c[4 * i + 3] = __fma_rn(w2, -0.75, -q);
 }
 
+// pow(w,2), pow(w,3) as the device evaluates them (exported for the tests: the CPU oracle is
+// pinned to these so that the comparison isolates everything but libdevice's pow)
+__global__ void pow23_kernel(const double *__restrict__ w, double *__restrict__ w2, double *__restrict__ w3, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    w2[i] = pow(w[i], 2.0);
+    w3[i] = pow(w[i], 3.0);
+}
+void launch_pow23(const double *w_dev, double *w2_dev, double *w3_dev, int n, cudaStream_t stream) {
+    pow23_kernel<<<(n + 127) / 128, 128, 0, stream>>>(w_dev, w2_dev, w3_dev, n);
+}
+
 void launch_bicubic_weights(const double *w_dev, double *c_dev, int n, cudaStream_t stream) {
     bicubic_weights_kernel<<<(n + 127) / 128, 128, 0, stream>>>(w_dev, c_dev, n);
 }

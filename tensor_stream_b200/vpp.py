@@ -88,6 +88,10 @@ def load_library():
     L.tsvpp_launch_count.restype = C.c_ulonglong
     L.tsvpp_describe_plan.argtypes = [vp, C.POINTER(TsvppFrame), C.POINTER(TsvppParams), C.c_char_p, C.c_size_t]
     L.tsvpp_describe_plan.restype = C.c_int
+    L.tsvpp_debug_pow23.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.tsvpp_debug_pow23.restype = C.c_int
+    L.tsvpp_last_error.argtypes = []
+    L.tsvpp_last_error.restype = C.c_char_p
     L.tsvpp_version.argtypes = []
     L.tsvpp_version.restype = C.c_char_p
     _lib = L
@@ -124,7 +128,24 @@ class FrameParameters:
 
 def _check(rc):
     if rc != 0:
-        raise VppError(str(rc))
+        e = VppError(str(rc))  # message is the bare status, like the reference's runtime_error
+        try:
+            e.detail = load_library().tsvpp_last_error().decode()
+        except Exception:
+            e.detail = ""
+        if e.detail:
+            e.add_note(e.detail)
+        raise e
+
+
+def device_pow23(w):
+    """pow(w,2), pow(w,3) evaluated on the current CUDA device (test hook)."""
+    import numpy as np
+    L = load_library()
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    w2, w3 = np.empty_like(w), np.empty_like(w)
+    _check(L.tsvpp_debug_pow23(w.ctypes.data, int(w.size), w2.ctypes.data, w3.ctypes.data))
+    return w2, w3
 
 
 def output_info(src_w, src_h, params):
