@@ -421,18 +421,16 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             }
             const int nslots = (need_uv ? 3 : 2) * cand_rp * K;
             const size_t stage = (size_t)nslots * stride;
-            const size_t fixed = 2 * (size_t)(3 * cand_rp * cand) + 8 * kMaxStages + 128;
+            const size_t fixed = 2 * 8 * kMaxStages + 128;
             int ns = 0;
-            if (!bulk) {
-                if (stage + fixed <= smem_cap) ns = 1;
-            } else {
-                const size_t budgets[3] = {72 * 1024, 110 * 1024, smem_cap};
+            {
+                const size_t budgets[3] = {56 * 1024, 110 * 1024, smem_cap};
                 for (size_t bgt : budgets) {
                     if (bgt > smem_cap) bgt = smem_cap;
                     if (bgt < fixed + stage) continue;
                     const int n = (int)((bgt - fixed) / stage);
-                    if (n >= 3 || (bgt == smem_cap && n >= 1)) {
-                        ns = std::min(n, want_ns > 0 ? want_ns : 6);
+                    if (n >= 2 || (bgt == smem_cap && n >= 1)) {
+                        ns = std::min(n, want_ns > 0 ? want_ns : 4);
                         ns = std::min(ns, kMaxStages);
                         break;
                     }
@@ -612,25 +610,25 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     pl->rs = rs;
     pl->ok = ok;
     pl->bulk = bulk;
-    pl->smem = fused_smem_bytes(D, bulk);
+    pl->smem = fused_smem_bytes(D);
     if (pl->smem > smem_cap) return TSVPP_UNSUPPORTED;
-    int rc = configure_fused(rs, ok, bulk, pl->smem);
+    int rc = configure_fused(rs, ok, bulk, smem_cap);
     if (rc) return rc;
-    pl->ctas_per_sm = std::max(1, max_ctas_per_sm(rs, ok, bulk, pl->smem));
+    pl->ctas_per_sm = std::max(1, max_ctas_per_sm(rs, ok, bulk, fused_block_threads(D), pl->smem));
     const int cap_ctas = env_int("TSVPP_CTAS_PER_SM", 0);
     if (cap_ctas > 0) pl->ctas_per_sm = std::min(pl->ctas_per_sm, cap_ctas);
     pl->out_w = dw;
     pl->out_h = dh;
     pl->out_elems = (size_t)(channels_of(p.fourcc) * dw * dh);
     pl->elem_size = (p.normalization || p.fourcc == TSVPP_HSV) ? 4 : 1;
-    pl->vec_ok_geom = (dw % 4 == 0) ? 1 : 0;
+    pl->vec_ok_geom = (dw % 2 == 0) ? 1 : 0;
     char buf[512];
     static const char *rs_names[] = {"nearest", "bilinear", "bicubic", "area"};
     std::snprintf(buf, sizeof(buf),
                   "resample=%s out_kind=%d fill=%s tw=%d rp=%d K=%d KX=%d ntiles=%d nstrips=%d slot_stride=%d "
-                  "stage_bytes=%d nstages=%d smem=%zu ctas_per_sm=%d crop=%d resize=%d",
+                  "stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d crop=%d resize=%d",
                   rs_names[rs], ok, bulk ? "bulk" : "ldg", tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
-                  nstages, pl->smem, pl->ctas_per_sm, (int)g.crop, (int)g.resize);
+                  nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize);
     pl->desc = buf;
     out = std::move(pl);
     return TSVPP_OK;

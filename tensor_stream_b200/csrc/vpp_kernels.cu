@@ -5,17 +5,21 @@
 // they pass through HBM (reference src/Crop.cu:4-21, src/Resize.cu:180-357,
 // src/ColorConversion.cu:6-278, dispatched by src/VideoProcessor.cpp:106-143).
 //
-// Structure (one persistent CTA loops over work items = (frame, strip of 2*rp output rows,
-// tile of tw output columns)):
-//   producer  : warp 0 issues one cp.async.bulk (TMA, SASS UBLKCP) per needed source-row
-//               segment into a ring of shared-memory stages, completion tracked by mbarriers;
-//               only the source rows / bytes the taps touch are ever fetched from HBM.
-//   phase A   : every thread resamples its output column from the staged rows with the
-//               reference's exact arithmetic (explicit __f*_rn intrinsics so the FMA positions
-//               equal the reference's nvcc -fmad=true contraction) and rounds through uint8 --
-//               the reference's NV12 intermediate lives in shared memory only.
-//   phase B   : 4 consecutive pixels per thread: BT.601 conversion, optional /255, layout;
-//               float4 / uchar4 stores.
+// Structure: persistent, warp-specialised CTAs loop over work items = (frame, strip of 2*rp
+// output rows, tile of tw output columns).
+//   producer warp : for each item, one cp.async.bulk (TMA unit, SASS UBLKCP) per needed
+//                   source-row segment into a ring of shared-memory stages; completion is
+//                   tracked by "full" mbarriers, reuse by "empty" mbarriers.  Only the source
+//                   rows / bytes the taps touch are ever fetched from HBM.
+//   consumer warps: each thread owns one 2x2 block of output pixels: 4 luma samples and the one
+//                   (U,V) pair they share are resampled from the staged rows with the
+//                   reference's exact arithmetic (explicit __f*_rn intrinsics so the FMA
+//                   positions equal the reference's nvcc -fmad=true contraction), rounded
+//                   through uint8 exactly where the reference stores its NV12 intermediate,
+//                   then converted (BT.601), normalised and stored with vector stores.
+//                   No block-wide barrier anywhere in the steady state.
+// uint8 <-> float conversions use the 2^23 magic-number form (LOP/FADD, full-rate pipes) instead
+// of I2F/F2I (quarter-rate XU pipe): ncu showed XU as the busiest pipe of the first version.
 // Bit-exactness contract: see oracle/vpp_oracle.c (same formulas, same citations).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,6 +47,9 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -72,18 +79,31 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 }
 
 // ---------------------------------------------------------------------------------------
+// Exact small-integer <-> float conversions on the FMA/ALU pipes
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kMagicBits = 0x4B000000u;  // 2^23 as float bits
+constexpr float kMagic = 8388608.0f;
+
+// (float)b for 0 <= b < 2^23, exact
+__device__ __forceinline__ float u2f(uint32_t b) { return __fsub_rn(__uint_as_float(kMagicBits | b), kMagic); }
+// bits of (2^23 + trunc(v)) for |v| < 2^22: (int)v == bits - kMagicBits when v >= 0; any negative
+// v yields bits < kMagicBits (only ever used before a clamp at 0)
+__device__ __forceinline__ int trunc_bits(float v) { return __float_as_int(__fadd_rz(v, kMagic)); }
+
+// ---------------------------------------------------------------------------------------
 // Arithmetic shared with the oracle (each cites the reference lines it reproduces)
 // ---------------------------------------------------------------------------------------
 
 // reference src/Resize.cu:5-25 (calculateBillinearInterpolation), FMA positions as compiled:
 //   v = fma(A*(1-wx), (1-wy), (B*wx)*(1-wy)); v = fma((1-wx), C*wy, v); v = fma(D, wx*wy, v)
-__device__ __forceinline__ int bilinear_px(int a, int b, int c, int d, float wx, float wy) {
-    const float A = (float)a, B = (float)b, C = (float)c, D = (float)d;
+// and (int)v stored to unsigned char (v in [0, 256)).
+__device__ __forceinline__ int bilinear_px(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float wx, float wy) {
+    const float A = u2f(a), B = u2f(b), C = u2f(c), D = u2f(d);
     const float omx = __fsub_rn(1.0f, wx), omy = __fsub_rn(1.0f, wy);
     float v = __fmaf_rn(__fmul_rn(A, omx), omy, __fmul_rn(__fmul_rn(B, wx), omy));
     v = __fmaf_rn(omx, __fmul_rn(C, wy), v);
     v = __fmaf_rn(D, __fmul_rn(wx, wy), v);
-    return __float2int_rz(v) & 0xFF;
+    return trunc_bits(v) & 0xFF;
 }
 
 // reference src/Resize.cu:45-59: one 4-tap row of the bicubic, DFMA chain as compiled
@@ -100,13 +120,15 @@ __device__ __forceinline__ int bicubic_dot(const double c0, const double c1, con
     return b;
 }
 
-// reference src/ColorConversion.cu:6-39 (NV12toRGB24Kernel); chroma terms are shared by the two
-// pixels of a pair.  R=(int)fma(Y',1.164,fma(V,1.596,.5)) etc.
+// reference src/ColorConversion.cu:6-39 (NV12toRGB24Kernel); chroma terms are shared by the
+// pixels of a 2x2 block.  R=(int)fma(Y',1.164,fma(V,1.596,.5)) etc..
 struct ChromaTerms {
     float r, g, b;
 };
 __device__ __forceinline__ ChromaTerms chroma_terms(int U, int V) {
-    const float fu = (float)(U - 128), fv = (float)(V - 128);
+    // (float)(U-128): exact via the magic form with a folded bias (2^23 + 128)
+    const float fu = __fsub_rn(__uint_as_float(kMagicBits | (uint32_t)U), kMagic + 128.0f);
+    const float fv = __fsub_rn(__uint_as_float(kMagicBits | (uint32_t)V), kMagic + 128.0f);
     ChromaTerms t;
     t.r = __fmaf_rn(fv, 1.5959997177f, 0.5f);
     t.b = __fmaf_rn(fu, 2.017999649f, 0.5f);
@@ -115,22 +137,27 @@ __device__ __forceinline__ ChromaTerms chroma_terms(int U, int V) {
     t.g = __fadd_rn(g, 0.5f);
     return t;
 }
-__device__ __forceinline__ void yuv_px(int Y, const ChromaTerms &t, int &R, int &G, int &B) {
-    const float yp = fmaxf(0.0f, __fsub_rn((float)Y, 16.0f));
-    R = min(max(__float2int_rz(__fmaf_rn(yp, 1.163999557f, t.r)), 0), 255);
-    G = min(max(__float2int_rz(__fmaf_rn(yp, 1.163999557f, t.g)), 0), 255);
-    B = min(max(__float2int_rz(__fmaf_rn(yp, 1.163999557f, t.b)), 0), 255);
+// one pixel -> the three channels as "magic" bit patterns clamped to [2^23+0, 2^23+255]
+__device__ __forceinline__ void yuv_px_bits(int Y, const ChromaTerms &t, int &R, int &G, int &B) {
+    // max(0, Y-16) on integers first: identical to max(0.f, (float)Y - 16.f)
+    const float yp = u2f((uint32_t)max(Y - 16, 0));
+    const int lo = (int)kMagicBits, hi = (int)kMagicBits + 255;
+    R = min(max(trunc_bits(__fmaf_rn(yp, 1.163999557f, t.r)), lo), hi);
+    G = min(max(trunc_bits(__fmaf_rn(yp, 1.163999557f, t.g)), lo), hi);
+    B = min(max(trunc_bits(__fmaf_rn(yp, 1.163999557f, t.b)), lo), hi);
 }
+__device__ __forceinline__ uint32_t bits_u8(int bits) { return (uint32_t)bits & 0xFFu; }
 
-// (float)c / 255.0f with IEEE rounding for c in 0..255: reciprocal multiply plus one residual
-// correction; verified exhaustively against the division (tests/test_host_logic.py).
-__device__ __forceinline__ float div255(int c) {
-    const float x = (float)c;
+// c / 255.0f with IEEE rounding for c in 0..255 given as magic bits: reciprocal multiply plus one
+// residual correction; verified exhaustively against the division (tests/test_host_logic.py).
+__device__ __forceinline__ float div255_x(float x) {
     const float r = 0x1.010102p-8f;  // RN(1/255)
     const float q = __fmul_rn(x, r);
     const float e = __fmaf_rn(-q, 255.0f, x);
     return __fmaf_rn(e, r, q);
 }
+__device__ __forceinline__ float div255_bits(int bits) { return div255_x(__fsub_rn(__int_as_float(bits), kMagic)); }
+__device__ __forceinline__ float div255_u8(uint32_t c) { return div255_x(u2f(c)); }
 
 // reference src/ColorConversion.cu:235-278 (RGBMergedToHSVMerged<float>)
 __device__ __forceinline__ void rgb_to_hsv(float R, float G, float B, float &H, float &S, float &V) {
@@ -155,7 +182,7 @@ __device__ __forceinline__ void rgb_to_hsv(float R, float G, float B, float &H, 
 }
 
 // ---------------------------------------------------------------------------------------
-// Stage fill
+// Stage fill (producer warp)
 // ---------------------------------------------------------------------------------------
 struct ItemCoord {
     int frame, strip, tile;
@@ -170,14 +197,14 @@ __device__ __forceinline__ ItemCoord decode_item(const PlanDev &P, int item) {
     return c;
 }
 
-// Producer: executed by warp 0.  One bulk copy per (output row of the strip, vertical tap).
+// One bulk copy per (output row of the strip, vertical tap).
 template <bool NEED_UV>
 __device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDev *__restrict__ frames, int item,
                                                  unsigned char *stage, uint64_t *bar, int lane, uint64_t policy) {
     const ItemCoord ic = decode_item(P, item);
     const FrameDev fr = frames[ic.frame];
-    const int nl = 2 * P.rp * P.K;                 // luma slots
-    const int nc = NEED_UV ? P.rp * P.K : 0;       // chroma slots
+    const int nl = 2 * P.rp * P.K;            // luma slots
+    const int nc = NEED_UV ? P.rp * P.K : 0;  // chroma slots
     const int a0l = P.seg_a0_l[ic.tile], lenl = P.seg_len_l[ic.tile];
     const int a0c = NEED_UV ? P.seg_a0_c[ic.tile] : 0, lenc = NEED_UV ? P.seg_len_c[ic.tile] : 0;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nl * lenl + nc * lenc));
@@ -198,10 +225,11 @@ __device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDe
 }
 
 // Fallback fill for frames whose base/pitch are not 16-byte aligned: guarded byte loads by the
-// whole CTA (correct for any alignment; bytes past the plane end read as 0).
+// producer warp (correct for any alignment; bytes past the plane end read as 0), then a plain
+// mbarrier arrive.  Slow path by design: NVDEC surfaces and torch tensors take the bulk path.
 template <bool NEED_UV>
 __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev *__restrict__ frames, int item,
-                                               unsigned char *stage, int tid) {
+                                               unsigned char *stage, uint64_t *bar, int lane) {
     const ItemCoord ic = decode_item(P, item);
     const FrameDev fr = frames[ic.frame];
     const int nl = 2 * P.rp * P.K;
@@ -211,7 +239,7 @@ __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev 
     for (int c = 0; c < nl; ++c) {
         const long base = (long)rs_l[c] * P.pitch_y + a0l;
         unsigned char *dst = stage + (size_t)c * P.slot_stride;
-        for (int b = tid; b < lenl; b += kThreads) {
+        for (int b = lane; b < lenl; b += 32) {
             const long g = base + b;
             dst[b] = (g < P.plane_bytes_y) ? __ldg(fr.y + g) : (unsigned char)0;
         }
@@ -222,16 +250,18 @@ __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev 
         for (int c = 0; c < nc; ++c) {
             const long base = (long)rs_c[c] * P.pitch_uv + a0c;
             unsigned char *dst = stage + (size_t)(nl + c) * P.slot_stride;
-            for (int b = tid; b < lenc; b += kThreads) {
+            for (int b = lane; b < lenc; b += 32) {
                 const long g = base + b;
                 dst[b] = (g < P.plane_bytes_uv) ? __ldg(fr.uv + g) : (unsigned char)0;
             }
         }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 
 // ---------------------------------------------------------------------------------------
-// Phase A: resample one output sample (one byte of the resized NV12 strip)
+// Resampling of one output sample (one byte of the reference's resized NV12 image)
 // ---------------------------------------------------------------------------------------
 template <int RS>
 struct ColOf;
@@ -246,298 +276,300 @@ struct ColOf<RS_AREA> { using T = ColArea; };
 
 // `slots` points at slot 0 of this output row; `orow` is the output row index used to look up
 // the vertical weights (luma: i, chroma: ci -- the reference evaluates the *luma-grid* formula
-// at the chroma index, src/Resize.cu:303-310), `stride` is 1 for luma and 2 for chroma bytes.
+// at the chroma index, src/Resize.cu:303-310), `stride` is 1 for luma and 2 for chroma bytes,
+// `wy` is the preloaded bilinear vertical weight.
 template <int RS>
 __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *slots,
-                                        const typename ColOf<RS>::T &col, int orow, int stride) {
+                                        const typename ColOf<RS>::T &col, int orow, int stride, float wy) {
     if constexpr (RS == RS_NEAREST) {
-        const ColNearest &c = col;
-        return slots[c.o];
+        return slots[col.o];
     } else if constexpr (RS == RS_BILINEAR) {
-        const ColBilinear &c = col;
         const unsigned char *s0 = slots, *s1 = slots + P.slot_stride;
-        const float wy = __ldg(P.wy + orow);
-        return bilinear_px(s0[c.o0], s0[c.o1], s1[c.o0], s1[c.o1], c.w, wy);
+        return bilinear_px(s0[col.o0], s0[col.o1], s1[col.o0], s1[col.o1], col.w, wy);
     } else if constexpr (RS == RS_BICUBIC) {
-        const ColBicubic &c = col;
+        const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
+        const double c0 = col.c[0], c1 = col.c[1], c2 = col.c[2], c3 = col.c[3];
         int b[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned char *s = slots + k * P.slot_stride;
-            b[k] = bicubic_dot(c.c[0], c.c[1], c.c[2], c.c[3], s[c.o[0]], s[c.o[1]], s[c.o[2]], s[c.o[3]]);
+            b[k] = bicubic_dot(c0, c1, c2, c3, s[o0], s[o1], s[o2], s[o3]);
         }
         const double *cy = P.cy + (size_t)orow * 4;
         return bicubic_dot(__ldg(cy + 0), __ldg(cy + 1), __ldg(cy + 2), __ldg(cy + 3), b[0], b[1], b[2], b[3]);
     } else {
         // reference src/Resize.cu:160-178 (calculateAreaInterpolation): rows outer, columns
         // inner; w = px*py; div += w; sum = fma(d, w, sum); (int)(sum/div)
-        const ColArea &c = col;
-        const float *px = P.px + (size_t)c.prow * P.KX;
+        const float *px = P.px + (size_t)col.prow * P.KX;
         const float *py = P.py + (size_t)(orow % P.PY) * P.K;
         float sum = 0.0f, div = 0.0f;
         for (int a = 0; a < P.K; ++a) {
-            const unsigned char *s = slots + a * P.slot_stride + c.o;
+            const unsigned char *s = slots + a * P.slot_stride + col.o;
             const float wyv = __ldg(py + a);
             for (int b = 0; b < P.KX; ++b) {
                 const float w = __fmul_rn(__ldg(px + b), wyv);
                 div = __fadd_rn(div, w);
-                sum = __fmaf_rn((float)s[b * stride], w, sum);
+                sum = __fmaf_rn(u2f(s[b * stride]), w, sum);
             }
         }
-        return __float2int_rz(__fdiv_rn(sum, div)) & 0xFF;
+        return trunc_bits(__fdiv_rn(sum, div)) & 0xFF;
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// Phase B: colour conversion + layout for 4 consecutive pixels of one output row
+// Colour conversion + layout for one 2x2 block of output pixels
 // ---------------------------------------------------------------------------------------
-template <int OK>
-__device__ __forceinline__ void emit4(const PlanDev &P, void *outp, int i, int j0, uint32_t y4, uint32_t uv4,
-                                      bool vec_ok) {
-    const int dw = P.dw, dh = P.dh;
-    const int nvalid = min(4, dw - j0);
-    int Yv[4] = {(int)(y4 & 0xFF), (int)((y4 >> 8) & 0xFF), (int)((y4 >> 16) & 0xFF), (int)(y4 >> 24)};
+__device__ __forceinline__ void st2f(float *p, float a, float b, bool vec, int nx) {
+    if (vec && nx == 2) {
+        __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b));
+    } else {
+        p[0] = a;
+        if (nx == 2) p[1] = b;
+    }
+}
+__device__ __forceinline__ void st2b(unsigned char *p, uint32_t a, uint32_t b, bool vec, int nx) {
+    if (vec && nx == 2) {
+        *reinterpret_cast<unsigned short *>(p) = (unsigned short)(a | (b << 8));
+    } else {
+        p[0] = (unsigned char)a;
+        if (nx == 2) p[1] = (unsigned char)b;
+    }
+}
 
-    if (OK == OUT_Y800_U8) {
-        unsigned char *o = (unsigned char *)outp + (size_t)i * dw + j0;
-        if (vec_ok && nvalid == 4) {
-            *reinterpret_cast<uint32_t *>(o) = y4;
-        } else {
-            for (int k = 0; k < nvalid; ++k) o[k] = (unsigned char)Yv[k];
-        }
-        return;
-    }
-    if (OK == OUT_Y800_F32) {
-        float *o = (float *)outp + (size_t)i * dw + j0;
-        float f[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = div255(Yv[k]);
-        if (vec_ok && nvalid == 4) {
-            __stcs(reinterpret_cast<float4 *>(o), make_float4(f[0], f[1], f[2], f[3]));
-        } else {
-            for (int k = 0; k < nvalid; ++k) o[k] = f[k];
-        }
-        return;
-    }
-    if (OK == OUT_NV12_U8 || OK == OUT_NV12_F32) {
+// Y[a][b]: resized luma of pixel (i0+a, j0+b); U,V: the block's chroma sample (0 if it does not
+// exist).  nx, ny: how many columns/rows of the block lie inside the image.
+template <int OK>
+__device__ __forceinline__ void emit2x2(const PlanDev &P, void *outp, int i0, int j0, const int (&Yv)[2][2], int U, int V,
+                                        int nx, int ny, bool vec) {
+    const int dw = P.dw, dh = P.dh;
+    if constexpr (OK == OUT_Y800_U8) {
+        for (int a = 0; a < ny; ++a)
+            st2b((unsigned char *)outp + (size_t)(i0 + a) * dw + j0, Yv[a][0], Yv[a][1], vec, nx);
+    } else if constexpr (OK == OUT_Y800_F32) {
+        for (int a = 0; a < ny; ++a)
+            st2f((float *)outp + (size_t)(i0 + a) * dw + j0, div255_u8(Yv[a][0]), div255_u8(Yv[a][1]), vec, nx);
+    } else if constexpr (OK == OUT_NV12_U8 || OK == OUT_NV12_F32) {
         // reference src/ColorConversion.cu:211-233 (NV12MergeBuffers): Y plane then UV plane
         const size_t wh = (size_t)dw * dh;
-        const bool do_uv = ((i & 1) == 0) && ((i >> 1) < P.ch2);
-        if (OK == OUT_NV12_U8) {
+        const bool has_uv = ((i0 >> 1) < P.ch2) && ((j0 >> 1) < P.cw2);
+        if constexpr (OK == OUT_NV12_U8) {
             unsigned char *o = (unsigned char *)outp;
-            for (int k = 0; k < nvalid; ++k) o[(size_t)i * dw + j0 + k] = (unsigned char)Yv[k];
-            if (do_uv)
-                for (int k = 0; k < nvalid; ++k)
-                    if (((j0 + k) >> 1) < P.cw2) o[wh + (size_t)(i >> 1) * dw + j0 + k] = (unsigned char)((uv4 >> (8 * k)) & 0xFF);
+            for (int a = 0; a < ny; ++a) st2b(o + (size_t)(i0 + a) * dw + j0, Yv[a][0], Yv[a][1], vec, nx);
+            if (has_uv) st2b(o + wh + (size_t)(i0 >> 1) * dw + j0, U, V, vec, 2);
         } else {
             float *o = (float *)outp;
-            for (int k = 0; k < nvalid; ++k) o[(size_t)i * dw + j0 + k] = div255(Yv[k]);
-            if (do_uv)
-                for (int k = 0; k < nvalid; ++k)
-                    if (((j0 + k) >> 1) < P.cw2) o[wh + (size_t)(i >> 1) * dw + j0 + k] = div255((int)((uv4 >> (8 * k)) & 0xFF));
+            for (int a = 0; a < ny; ++a)
+                st2f(o + (size_t)(i0 + a) * dw + j0, div255_u8(Yv[a][0]), div255_u8(Yv[a][1]), vec, nx);
+            if (has_uv) st2f(o + wh + (size_t)(i0 >> 1) * dw + j0, div255_u8(U), div255_u8(V), vec, 2);
         }
-        return;
-    }
-
-    // RGB family
-    const ChromaTerms t0 = chroma_terms((int)(uv4 & 0xFF), (int)((uv4 >> 8) & 0xFF));
-    const ChromaTerms t1 = chroma_terms((int)((uv4 >> 16) & 0xFF), (int)(uv4 >> 24));
-    int R[4], G[4], B[4];
-    yuv_px(Yv[0], t0, R[0], G[0], B[0]);
-    yuv_px(Yv[1], t0, R[1], G[1], B[1]);
-    yuv_px(Yv[2], t1, R[2], G[2], B[2]);
-    yuv_px(Yv[3], t1, R[3], G[3], B[3]);
-
-    if (OK == OUT_HSV_F32) {
-        // reference src/ColorConversion.cu:360-372: from normalised RGB (never BGR), merged
-        float *o = (float *)outp + ((size_t)i * dw + j0) * 3;
-        float v[12];
+    } else {
+        // RGB family
+        const ChromaTerms t = chroma_terms(U, V);
+        int R[2][2], G[2][2], B[2][2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rgb_to_hsv(div255(R[k]), div255(G[k]), div255(B[k]), v[3 * k], v[3 * k + 1], v[3 * k + 2]);
-        if (vec_ok && nvalid == 4) {
-            float4 *o4 = reinterpret_cast<float4 *>(o);
-            __stcs(o4 + 0, make_float4(v[0], v[1], v[2], v[3]));
-            __stcs(o4 + 1, make_float4(v[4], v[5], v[6], v[7]));
-            __stcs(o4 + 2, make_float4(v[8], v[9], v[10], v[11]));
-        } else {
-            for (int k = 0; k < 3 * nvalid; ++k) o[k] = v[k];
-        }
-        return;
-    }
-
-    if (P.swap_rb) {
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int t = R[k];
-            R[k] = B[k];
-            B[k] = t;
-        }
-    }
-    if (OK == OUT_RGB_PLANAR_F32) {
-        const size_t plane = (size_t)dw * dh;
-        float *o = (float *)outp + (size_t)i * dw + j0;
-        if (vec_ok && nvalid == 4) {
-            __stcs(reinterpret_cast<float4 *>(o), make_float4(div255(R[0]), div255(R[1]), div255(R[2]), div255(R[3])));
-            __stcs(reinterpret_cast<float4 *>(o + plane), make_float4(div255(G[0]), div255(G[1]), div255(G[2]), div255(G[3])));
-            __stcs(reinterpret_cast<float4 *>(o + 2 * plane), make_float4(div255(B[0]), div255(B[1]), div255(B[2]), div255(B[3])));
-        } else {
-            for (int k = 0; k < nvalid; ++k) {
-                o[k] = div255(R[k]);
-                o[plane + k] = div255(G[k]);
-                o[2 * plane + k] = div255(B[k]);
+            for (int b = 0; b < 2; ++b) yuv_px_bits(Yv[a][b], t, R[a][b], G[a][b], B[a][b]);
+
+        if constexpr (OK == OUT_HSV_F32) {
+            // reference src/ColorConversion.cu:360-372: from normalised RGB (never BGR), merged
+            for (int a = 0; a < ny; ++a) {
+                float h[2][3];
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+                    rgb_to_hsv(div255_bits(R[a][b]), div255_bits(G[a][b]), div255_bits(B[a][b]), h[b][0], h[b][1], h[b][2]);
+                float *o = (float *)outp + ((size_t)(i0 + a) * dw + j0) * 3;
+                if (vec && nx == 2) {
+                    __stcs(reinterpret_cast<float2 *>(o), make_float2(h[0][0], h[0][1]));
+                    __stcs(reinterpret_cast<float2 *>(o) + 1, make_float2(h[0][2], h[1][0]));
+                    __stcs(reinterpret_cast<float2 *>(o) + 2, make_float2(h[1][1], h[1][2]));
+                } else {
+                    for (int b = 0; b < nx; ++b) {
+                        o[3 * b] = h[b][0];
+                        o[3 * b + 1] = h[b][1];
+                        o[3 * b + 2] = h[b][2];
+                    }
+                }
             }
+            return;
         }
-    } else if (OK == OUT_RGB_PLANAR_U8) {
-        const size_t plane = (size_t)dw * dh;
-        unsigned char *o = (unsigned char *)outp + (size_t)i * dw + j0;
-        if (vec_ok && nvalid == 4) {
-            *reinterpret_cast<uint32_t *>(o) = (uint32_t)R[0] | ((uint32_t)R[1] << 8) | ((uint32_t)R[2] << 16) | ((uint32_t)R[3] << 24);
-            *reinterpret_cast<uint32_t *>(o + plane) = (uint32_t)G[0] | ((uint32_t)G[1] << 8) | ((uint32_t)G[2] << 16) | ((uint32_t)G[3] << 24);
-            *reinterpret_cast<uint32_t *>(o + 2 * plane) = (uint32_t)B[0] | ((uint32_t)B[1] << 8) | ((uint32_t)B[2] << 16) | ((uint32_t)B[3] << 24);
-        } else {
-            for (int k = 0; k < nvalid; ++k) {
-                o[k] = (unsigned char)R[k];
-                o[plane + k] = (unsigned char)G[k];
-                o[2 * plane + k] = (unsigned char)B[k];
+        if (P.swap_rb) {  // BGR (ColorConversion.cu:304-305): first channel is B
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int tmp = R[a][b];
+                    R[a][b] = B[a][b];
+                    B[a][b] = tmp;
+                }
+        }
+        if constexpr (OK == OUT_RGB_PLANAR_F32) {
+            const size_t plane = (size_t)dw * dh;
+            for (int a = 0; a < ny; ++a) {
+                float *o = (float *)outp + (size_t)(i0 + a) * dw + j0;
+                st2f(o, div255_bits(R[a][0]), div255_bits(R[a][1]), vec, nx);
+                st2f(o + plane, div255_bits(G[a][0]), div255_bits(G[a][1]), vec, nx);
+                st2f(o + 2 * plane, div255_bits(B[a][0]), div255_bits(B[a][1]), vec, nx);
             }
-        }
-    } else if (OK == OUT_RGB_MERGED_F32) {
-        float *o = (float *)outp + ((size_t)i * dw + j0) * 3;
-        if (vec_ok && nvalid == 4) {
-            float4 *o4 = reinterpret_cast<float4 *>(o);
-            __stcs(o4 + 0, make_float4(div255(R[0]), div255(G[0]), div255(B[0]), div255(R[1])));
-            __stcs(o4 + 1, make_float4(div255(G[1]), div255(B[1]), div255(R[2]), div255(G[2])));
-            __stcs(o4 + 2, make_float4(div255(B[2]), div255(R[3]), div255(G[3]), div255(B[3])));
-        } else {
-            for (int k = 0; k < nvalid; ++k) {
-                o[3 * k] = div255(R[k]);
-                o[3 * k + 1] = div255(G[k]);
-                o[3 * k + 2] = div255(B[k]);
+        } else if constexpr (OK == OUT_RGB_PLANAR_U8) {
+            const size_t plane = (size_t)dw * dh;
+            for (int a = 0; a < ny; ++a) {
+                unsigned char *o = (unsigned char *)outp + (size_t)(i0 + a) * dw + j0;
+                st2b(o, bits_u8(R[a][0]), bits_u8(R[a][1]), vec, nx);
+                st2b(o + plane, bits_u8(G[a][0]), bits_u8(G[a][1]), vec, nx);
+                st2b(o + 2 * plane, bits_u8(B[a][0]), bits_u8(B[a][1]), vec, nx);
             }
-        }
-    } else if (OK == OUT_RGB_MERGED_U8) {
-        unsigned char *o = (unsigned char *)outp + ((size_t)i * dw + j0) * 3;
-        if (vec_ok && nvalid == 4) {
-            uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
-            o4[0] = (uint32_t)R[0] | ((uint32_t)G[0] << 8) | ((uint32_t)B[0] << 16) | ((uint32_t)R[1] << 24);
-            o4[1] = (uint32_t)G[1] | ((uint32_t)B[1] << 8) | ((uint32_t)R[2] << 16) | ((uint32_t)G[2] << 24);
-            o4[2] = (uint32_t)B[2] | ((uint32_t)R[3] << 8) | ((uint32_t)G[3] << 16) | ((uint32_t)B[3] << 24);
-        } else {
-            for (int k = 0; k < nvalid; ++k) {
-                o[3 * k] = (unsigned char)R[k];
-                o[3 * k + 1] = (unsigned char)G[k];
-                o[3 * k + 2] = (unsigned char)B[k];
+        } else if constexpr (OK == OUT_RGB_MERGED_F32) {
+            for (int a = 0; a < ny; ++a) {
+                float *o = (float *)outp + ((size_t)(i0 + a) * dw + j0) * 3;
+                if (vec && nx == 2) {
+                    __stcs(reinterpret_cast<float2 *>(o), make_float2(div255_bits(R[a][0]), div255_bits(G[a][0])));
+                    __stcs(reinterpret_cast<float2 *>(o) + 1, make_float2(div255_bits(B[a][0]), div255_bits(R[a][1])));
+                    __stcs(reinterpret_cast<float2 *>(o) + 2, make_float2(div255_bits(G[a][1]), div255_bits(B[a][1])));
+                } else {
+                    for (int b = 0; b < nx; ++b) {
+                        o[3 * b] = div255_bits(R[a][b]);
+                        o[3 * b + 1] = div255_bits(G[a][b]);
+                        o[3 * b + 2] = div255_bits(B[a][b]);
+                    }
+                }
+            }
+        } else if constexpr (OK == OUT_RGB_MERGED_U8) {
+            for (int a = 0; a < ny; ++a) {
+                unsigned char *o = (unsigned char *)outp + ((size_t)(i0 + a) * dw + j0) * 3;
+                if (vec && nx == 2) {
+                    unsigned short *o2 = reinterpret_cast<unsigned short *>(o);
+                    o2[0] = (unsigned short)(bits_u8(R[a][0]) | (bits_u8(G[a][0]) << 8));
+                    o2[1] = (unsigned short)(bits_u8(B[a][0]) | (bits_u8(R[a][1]) << 8));
+                    o2[2] = (unsigned short)(bits_u8(G[a][1]) | (bits_u8(B[a][1]) << 8));
+                } else {
+                    for (int b = 0; b < nx; ++b) {
+                        o[3 * b] = (unsigned char)bits_u8(R[a][b]);
+                        o[3 * b + 1] = (unsigned char)bits_u8(G[a][b]);
+                        o[3 * b + 2] = (unsigned char)bits_u8(B[a][b]);
+                    }
+                }
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// The fused kernel
+// The fused kernel.  blockDim.x = 32 (producer warp) + round_up(tw/2 * rp, 32) consumers.
 // ---------------------------------------------------------------------------------------
 template <int RS, int OK, bool BULK>
-__global__ void __launch_bounds__(kThreads) vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
-                                                             int nframes, int vec_ok) {
+__global__ void __launch_bounds__(kMaxThreads, (RS == RS_BICUBIC || RS == RS_AREA) ? 2 : 4) vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
+                                                                int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     using ColT = typename ColOf<RS>::T;
+    constexpr bool SMALL_COL = sizeof(ColT) <= 16;
     extern __shared__ __align__(128) unsigned char smem[];
 
-    const int tid = threadIdx.x;
-    const int NS = BULK ? P.nstages : 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NS = P.nstages;
     unsigned char *stages = smem;
-    const int rbuf_bytes = 3 * P.rp * P.tw;
-    unsigned char *rbuf = smem + (size_t)NS * P.stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(rbuf + 2 * rbuf_bytes);  // rbuf_bytes is a multiple of 32
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * P.stage_bytes);
+    uint64_t *empty = full + kMaxStages;
+    const int ncons_warps = ((int)blockDim.x >> 5) - 1;
 
     const int total = nframes * P.nstrips * P.ntiles;
     const int first = blockIdx.x;
-    if (first >= total) return;
-    const int my_items = (total - first + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_items = first < total ? (total - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    uint64_t policy = 0;
-    if (BULK) {
-        if (tid == 0) {
-            for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
-            fence_barrier_init();
-            fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, (uint32_t)ncons_warps);
         }
-        __syncthreads();
-        if (tid < 32) {
-            policy = l2_policy_evict_first();
-            for (int p = 0; p < NS - 1 && p < my_items; ++p)
-                issue_stage_bulk<NEED_UV>(P, frames, first + p * gridDim.x, stages + (size_t)p * P.stage_bytes, bars + p,
-                                          tid, policy);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= producer =================
+        const uint64_t policy = l2_policy_evict_first();
+        for (int it = 0; it < my_items; ++it) {
+            const int s = it % NS;
+            mbar_wait(empty + s, (uint32_t)(((it / NS) & 1) ^ 1));  // stage free (passes at once the first round)
+            unsigned char *stage = stages + (size_t)s * P.stage_bytes;
+            if (BULK)
+                issue_stage_bulk<NEED_UV>(P, frames, first + it * gridDim.x, stage, full + s, lane, policy);
+            else
+                fill_stage_ldg<NEED_UV>(P, frames, first + it * gridDim.x, stage, full + s, lane);
         }
+        return;
     }
 
-    const int tw = P.tw;
-    const int tx = tid & (tw - 1);
-    const int ty = tid / tw;
-    const int ny = kThreads / tw;
-    const int nrg = (NEED_UV ? 3 : 2) * P.rp;  // row groups per strip: 2*rp luma (+ rp chroma)
-    const int units_per_row = tw >> 2;
+    // ================= consumers =================
+    const int ctid = tid - 32;
+    const int half_tw = P.tw >> 1;
+    const int tx = ctid % half_tw;  // column pair inside the tile
+    const int ty = ctid / half_tw;  // row pair inside the strip
+    const bool active = ty < P.rp;
+    const bool vec = vec_ok != 0;
+    const ColT *col_l = reinterpret_cast<const ColT *>(P.col_l);
+    const ColT *col_c = reinterpret_cast<const ColT *>(P.col_c);
+
+    int cur_tile = -1;
+    ColT l0, l1, c0, c1;  // column parameters (kept in registers when small)
 
     for (int it = 0; it < my_items; ++it) {
         const int item = first + it * gridDim.x;
         const ItemCoord ic = decode_item(P, item);
-        unsigned char *stage;
-        if (BULK) {
-            const int pf = it + NS - 1;
-            if (tid < 32 && pf < my_items) {
-                const int ps = pf % NS;
-                issue_stage_bulk<NEED_UV>(P, frames, first + pf * gridDim.x, stages + (size_t)ps * P.stage_bytes,
-                                          bars + ps, tid, policy);
+        const int s = it % NS;
+        const unsigned char *stage = stages + (size_t)s * P.stage_bytes;
+        const int colbase = ic.tile * P.tw + 2 * tx;
+        const int i0 = (ic.strip * P.rp + ty) * 2;  // first output row of this thread's block
+        const int ci = ic.strip * P.rp + ty;        // its chroma row
+        const int j0 = colbase;                     // first output column
+        float wy0 = 0.f, wy1 = 0.f, wyc = 0.f;
+        if (active) {
+            if (SMALL_COL && ic.tile != cur_tile) {
+                l0 = col_l[colbase];
+                l1 = col_l[colbase + 1];
+                if (NEED_UV) {
+                    c0 = col_c[colbase];
+                    c1 = col_c[colbase + 1];
+                }
+                cur_tile = ic.tile;
             }
-            stage = stages + (size_t)(it % NS) * P.stage_bytes;
-        } else {
-            stage = stages;
-            fill_stage_ldg<NEED_UV>(P, frames, item, stage, tid);
-        }
-
-        // column parameters of this thread (issued before the barrier wait so the latency hides)
-        const int col = ic.tile * tw + tx;
-        ColT cl = reinterpret_cast<const ColT *>(P.col_l)[col];
-        ColT cc;
-        if (NEED_UV) cc = reinterpret_cast<const ColT *>(P.col_c)[col];
-
-        if (BULK)
-            mbar_wait(bars + (it % NS), (uint32_t)((it / NS) & 1));
-        else
-            __syncthreads();
-
-        // ---- phase A: resized NV12 strip -> rbuf (bytes) ----
-        unsigned char *rb = rbuf + (size_t)(it & 1) * rbuf_bytes;
-        for (int rg = ty; rg < nrg; rg += ny) {
-            int v = 0;
-            if (rg < 2 * P.rp) {
-                const int i = ic.strip * 2 * P.rp + rg;
-                if (i < P.dh && col < P.dw)
-                    v = resample<RS>(P, stage + (size_t)rg * P.K * P.slot_stride, cl, i, 1);
-            } else if (NEED_UV) {
-                const int ci = ic.strip * P.rp + (rg - 2 * P.rp);
-                if (ci < P.ch2 && (col >> 1) < P.cw2)
-                    v = resample<RS>(P, stage + (size_t)rg * P.K * P.slot_stride, cc, ci, 2);
-            }
-            rb[rg * tw + tx] = (unsigned char)v;
-        }
-        __syncthreads();
-
-        // ---- phase B: colour conversion + layout ----
-        void *outp = frames[ic.frame].out;
-        const int nunits = 2 * P.rp * units_per_row;
-        for (int u = tid; u < nunits; u += kThreads) {
-            const int r = u / units_per_row;
-            const int c4 = u - r * units_per_row;
-            const int i = ic.strip * 2 * P.rp + r;
-            const int j0 = ic.tile * tw + 4 * c4;
-            if (i < P.dh && j0 < P.dw) {
-                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(rb + r * tw + 4 * c4);
-                const uint32_t uv4 =
-                    NEED_UV ? *reinterpret_cast<const uint32_t *>(rb + (2 * P.rp + (r >> 1)) * tw + 4 * c4) : 0u;
-                emit4<OK>(P, outp, i, j0, y4, uv4, vec_ok != 0);
+            if (RS == RS_BILINEAR) {
+                wy0 = __ldg(P.wy + i0);
+                wy1 = __ldg(P.wy + i0 + 1);
+                wyc = __ldg(P.wy + ci);
             }
         }
-        if (!BULK) __syncthreads();  // stage is refilled by everyone next iteration
+
+        mbar_wait(full + s, (uint32_t)((it / NS) & 1));
+
+        int Yv[2][2] = {{0, 0}, {0, 0}};
+        int U = 0, V = 0;
+        const int nx = min(2, P.dw - j0), ny = min(2, P.dh - i0);
+        if (active && nx > 0 && ny > 0) {
+            const unsigned char *sl0 = stage + (size_t)((2 * ty) * P.K) * P.slot_stride;
+            const unsigned char *sl1 = sl0 + (size_t)P.K * P.slot_stride;
+            const ColT &L0 = SMALL_COL ? l0 : col_l[colbase];
+            const ColT &L1 = SMALL_COL ? l1 : col_l[colbase + 1];
+            Yv[0][0] = resample<RS>(P, sl0, L0, i0, 1, wy0);
+            if (nx > 1) Yv[0][1] = resample<RS>(P, sl0, L1, i0, 1, wy0);
+            if (ny > 1) {
+                Yv[1][0] = resample<RS>(P, sl1, L0, i0 + 1, 1, wy1);
+                if (nx > 1) Yv[1][1] = resample<RS>(P, sl1, L1, i0 + 1, 1, wy1);
+            }
+            if (NEED_UV && ci < P.ch2 && (j0 >> 1) < P.cw2) {
+                const unsigned char *sc = stage + (size_t)((2 * P.rp + ty) * P.K) * P.slot_stride;
+                const ColT &C0 = SMALL_COL ? c0 : col_c[colbase];
+                const ColT &C1 = SMALL_COL ? c1 : col_c[colbase + 1];
+                U = resample<RS>(P, sc, C0, ci, 2, wyc);
+                V = resample<RS>(P, sc, C1, ci, 2, wyc);
+            }
+        }
+        // all shared-memory reads of this stage are done: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+
+        if (active && nx > 0 && ny > 0) emit2x2<OK>(P, frames[ic.frame].out, i0, j0, Yv, U, V, nx, ny, vec);
     }
 }
 
@@ -609,25 +641,33 @@ static KernelFn pick_kernel(int rs, int ok, bool bulk) {
     return nullptr;
 }
 
-size_t fused_smem_bytes(const PlanDev &P, bool bulk) {
-    const int NS = bulk ? P.nstages : 1;
-    return (size_t)NS * P.stage_bytes + 2 * (size_t)(3 * P.rp * P.tw) + 8 * kMaxStages + 128;
+int fused_block_threads(const PlanDev &P) {
+    const int cons = (P.tw / 2) * P.rp;
+    return 32 + (cons + 31) / 32 * 32;
 }
 
-int configure_fused(int rs, int ok, bool bulk, size_t smem_bytes) {
+size_t fused_smem_bytes(const PlanDev &P) {
+    return (size_t)P.nstages * P.stage_bytes + 2 * 8 * kMaxStages + 128;
+}
+
+// the dynamic-shared-memory opt-in is a per-FUNCTION attribute shared by every plan that uses
+// the instantiation: always raise it to the device maximum
+int configure_fused(int rs, int ok, bool bulk, size_t smem_optin_max) {
     KernelFn fn = pick_kernel(rs, ok, bulk);
     if (!fn) return (int)cudaErrorMissingConfiguration;  // reference ColorConversion.cu:376
     return (int)cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes);
+                                     (int)smem_optin_max);
 }
 
-int max_ctas_per_sm(int rs, int ok, bool bulk, size_t smem_bytes) {
+int max_ctas_per_sm(int rs, int ok, bool bulk, int threads, size_t smem_bytes) {
     KernelFn fn = pick_kernel(rs, ok, bulk);
     if (!fn) return 0;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reinterpret_cast<const void *>(fn), kThreads, smem_bytes) !=
-        cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reinterpret_cast<const void *>(fn), threads, smem_bytes) !=
+        cudaSuccess) {
+        (void)cudaGetLastError();
         return 0;
+    }
     return n;
 }
 
@@ -635,7 +675,7 @@ int launch_fused(int rs, int ok, bool bulk, const PlanDev &P, const FrameDev *fr
                  int grid, size_t smem_bytes, cudaStream_t stream) {
     KernelFn fn = pick_kernel(rs, ok, bulk);
     if (!fn) return (int)cudaErrorMissingConfiguration;
-    fn<<<grid, kThreads, smem_bytes, stream>>>(P, frames_dev, nframes, vec_ok);
+    fn<<<grid, fused_block_threads(P), smem_bytes, stream>>>(P, frames_dev, nframes, vec_ok);
     return (int)cudaGetLastError();
 }
 

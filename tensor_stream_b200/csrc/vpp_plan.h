@@ -33,7 +33,7 @@ enum OutKind : int {
     OUT_COUNT = 9
 };
 
-constexpr int kThreads = 256;       // threads per CTA
+constexpr int kMaxThreads = 288;    // 1 producer warp + up to 256 consumer threads (one 2x2 block each)
 constexpr int kMaxStages = 8;       // mbarrier ring depth upper bound
 
 // column parameters, one per output sample column (luma: per output x; chroma: per chroma byte)
