@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "192")),
-                    help="frames in the device-resident pool = frames per step (192 x 3.1 MB = 597 MB >> L2)")
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("BENCH_FRAMES", "768")),
+                    help="frames in the device-resident pool = frames per step (768 x 3.1 MB = 2.4 GB >> L2)")
     ap.add_argument("--e2e-frames", type=int, default=64, help="frames per end-to-end step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -213,6 +213,7 @@ def swscale_baseline(cores, seconds=6.0):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from tensor_stream_b200 import sharding as S
     from tensor_stream_b200 import vpp
 
     rank, local, world = dist_env()
@@ -284,21 +285,32 @@ def run_ours(args):
     hout = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(ne)]
     hframes = list(zip(hy, huv))
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        v.convert_batch_host(hframes, fp, W, H, hout)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        v.convert_batch_host(hframes, fp, W, H, hout)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    # result really came back: spot-check one output against the device path
-    assert torch.equal(hout[0], outs[0].cpu()), "e2e output differs from the device path"
+    fetch = int(plan.split("fetch_bytes_per_frame=")[1].split()[0]) if "fetch_bytes_per_frame=" in plan else None
+    e2e_runs = {}
+    for mode, envv in (("zero_copy", "1"), ("staged_h2d", "0")):
+        # zero_copy: the kernel reads pinned host memory in place (only the rows it needs cross PCIe);
+        # staged_h2d: whole frames are cudaMemcpy'd to device staging first.  Both end with D2H copies.
+        os.environ["TSVPP_HOST_ZEROCOPY"] = envv
+        for _ in range(2):
+            v.convert_batch_host(hframes, fp, W, H, hout)
+        path = v.last_host_path()
+        for o in hout:
+            o.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            v.convert_batch_host(hframes, fp, W, H, hout)
+        torch.cuda.synchronize()
+        e2e_runs[mode] = (time.perf_counter() - t0, path)
+        # the result really came back to the host: check it against the device path
+        assert torch.equal(hout[0], outs[0].cpu()) and torch.equal(hout[-1], outs[(ne - 1) % n].cpu()), \
+            "e2e output differs from the device path"
+    os.environ.pop("TSVPP_HOST_ZEROCOPY", None)
+    best_mode = min(e2e_runs, key=lambda k: e2e_runs[k][0])
+    e2e_s = e2e_runs[best_mode][0]
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, e2e_zc_ms, e2e_st_ms = S.max_over_ranks(
+        [total_ms, e2e_s * 1e3, e2e_runs["zero_copy"][0] * 1e3, e2e_runs["staged_h2d"][0] * 1e3], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -319,9 +331,16 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (pool %d MB vs 126 MB), cycled, no flush" % round(n * W * H * 1.5 / 1e6),
                    "parallelism": "dp%d: independent frame pool per GPU, no collective" % world,
                    "launches_per_step": 1, "plan": plan},
-        "e2e": {"value": e2e_fps, "unit": "frames/sec", "h2d_bytes_per_step": ne * W * H * 3 // 2,
+        "e2e": {"value": e2e_fps, "unit": "frames/sec",
+                "h2d_bytes_per_step": ne * (fetch if (best_mode == "zero_copy" and fetch) else W * H * 3 // 2),
                 "d2h_bytes_per_step": ne * DW * DH * 3 * 4, "frames_per_step": ne, "steps": e2e_steps,
-                "api": "tsvpp_convert_batch_host (pinned host NV12 in, host float32 out)"},
+                "api": "tsvpp_convert_batch_host (pinned host NV12 in, host float32 out)",
+                "path": best_mode,
+                "zero_copy_fps": world * ne * e2e_steps / (e2e_zc_ms * 1e-3),
+                "staged_h2d_fps": world * ne * e2e_steps / (e2e_st_ms * 1e-3),
+                "note": "zero_copy: the fused kernel reads the pinned host frames in place, so only the source rows its "
+                        "taps touch cross PCIe (h2d bytes = plan fetch_bytes_per_frame); staged_h2d: whole-frame cudaMemcpy "
+                        "(h2d bytes = full NV12 frame); both include the D2H copy of every output"},
         "gpu_launches": int(launches) * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"),

@@ -210,7 +210,8 @@ static double g_pw[POW_TAB_CAP], g_pw2[POW_TAB_CAP], g_pw3[POW_TAB_CAP];
 static int g_pow_n = 0;       /* installed entries (open addressing, cap POW_TAB_CAP) */
 static uint8_t g_pow_used[POW_TAB_CAP];
 static int g_pow_record = 0;
-static double g_rec[POW_TAB_CAP];
+static double g_rec[POW_TAB_CAP], g_rec_key[POW_TAB_CAP];
+static uint8_t g_rec_used[POW_TAB_CAP];
 static int g_rec_n = 0;
 
 static inline uint32_t pow_hash(double w) {
@@ -240,7 +241,10 @@ int vpo_pow_table_set(const double *w, const double *w2, const double *w3, int n
 }
 void vpo_pow_record(int on) {
     g_pow_record = on;
-    if (on) g_rec_n = 0;
+    if (on) {
+        g_rec_n = 0;
+        memset(g_rec_used, 0, sizeof(g_rec_used));
+    }
 }
 int vpo_pow_recorded(double *out, int cap) {
     int n = g_rec_n < cap ? g_rec_n : cap;
@@ -249,9 +253,17 @@ int vpo_pow_recorded(double *out, int cap) {
 }
 static void pow23(double w, double *w2, double *w3) {
     if (g_pow_record) {
+        uint32_t h = pow_hash(w);
         int seen = 0;
-        for (int i = g_rec_n - 1; i >= 0 && i >= g_rec_n - 8; i--) seen |= (g_rec[i] == w);
-        if (!seen && g_rec_n < POW_TAB_CAP) g_rec[g_rec_n++] = w;
+        while (g_rec_used[h]) {
+            if (g_rec_key[h] == w) { seen = 1; break; }
+            h = (h + 1) & (POW_TAB_CAP - 1);
+        }
+        if (!seen && g_rec_n < POW_TAB_CAP / 2) {
+            g_rec_used[h] = 1;
+            g_rec_key[h] = w;
+            g_rec[g_rec_n++] = w;
+        }
     }
     if (g_pow_n) {
         uint32_t h = pow_hash(w);

@@ -233,7 +233,8 @@ struct Plan {
     int out_w = 0, out_h = 0;
     size_t out_elems = 0;
     int elem_size = 1;
-    int vec_ok_geom = 0;  // dw % 4 == 0
+    int vec_ok_geom = 0;  // dw % 2 == 0
+    long fetch_bytes_per_frame = 0;
     void *dev_tables = nullptr;
     std::string desc;
     ~Plan() {
@@ -262,6 +263,7 @@ struct TsvppContext {
     unsigned char *stage_in[2] = {};
     unsigned char *stage_out[2] = {};
     size_t stage_in_cap[2] = {}, stage_out_cap[2] = {};
+    int last_host_zero_copy = 0;
     cudaEvent_t hev[2] = {};
 };
 
@@ -622,13 +624,18 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     pl->out_elems = (size_t)(channels_of(p.fourcc) * dw * dh);
     pl->elem_size = (p.normalization || p.fourcc == TSVPP_HSV) ? 4 : 1;
     pl->vec_ok_geom = (dw % 2 == 0) ? 1 : 0;
-    char buf[512];
+    // bytes one frame's work items fetch from the source planes (what crosses HBM / PCIe)
+    long fetch = 0;
+    for (int t = 0; t < ntiles; ++t)
+        fetch += (long)nstrips * ((long)2 * rp * K * lenl[t] + (need_uv ? (long)rp * K * lenc[t] : 0));
+    pl->fetch_bytes_per_frame = fetch;
+    char buf[640];
     static const char *rs_names[] = {"nearest", "bilinear", "bicubic", "area"};
     std::snprintf(buf, sizeof(buf),
                   "resample=%s out_kind=%d fill=%s tw=%d rp=%d K=%d KX=%d ntiles=%d nstrips=%d slot_stride=%d "
-                  "stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d crop=%d resize=%d",
+                  "stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d crop=%d resize=%d fetch_bytes_per_frame=%ld",
                   rs_names[rs], ok, bulk ? "bulk" : "ldg", tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
-                  nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize);
+                  nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize, fetch);
     pl->desc = buf;
     out = std::move(pl);
     return TSVPP_OK;
@@ -937,6 +944,33 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
             ctx->stage_out_cap[s] = out_frame * chunk;
         }
     }
+    // Zero-copy input: when every input plane lives in pinned (page-locked, device-mapped) host
+    // memory the fused kernel reads it in place over PCIe -- its bulk copies fetch only the source
+    // rows the taps touch (1.47 of 3.11 MB per 1080p frame for the 256x256 bilinear case), which a
+    // whole-frame cudaMemcpy cannot do.  Pageable inputs go through staged H2D copies.
+    bool zero_copy = env_int("TSVPP_HOST_ZEROCOPY", 1) != 0;
+    std::vector<const uint8_t *> zy, zuv;
+    if (zero_copy) {
+        zy.resize(n);
+        zuv.resize(n);
+        for (int i = 0; i < n && zero_copy; ++i) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, frames[i].y) != cudaSuccess || a.type != cudaMemoryTypeHost ||
+                !a.devicePointer) {
+                zero_copy = false;
+                break;
+            }
+            zy[i] = (const uint8_t *)a.devicePointer;
+            if (cudaPointerGetAttributes(&a, frames[i].uv) != cudaSuccess || a.type != cudaMemoryTypeHost ||
+                !a.devicePointer) {
+                zero_copy = false;
+                break;
+            }
+            zuv[i] = (const uint8_t *)a.devicePointer;
+        }
+        (void)cudaGetLastError();
+    }
+    ctx->last_host_zero_copy = zero_copy ? 1 : 0;
     std::vector<TsvppFrame> dframes(chunk);
     std::vector<void *> douts(chunk);
     int which = 0;
@@ -944,13 +978,18 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
         const int m = std::min(chunk, n - base);
         cudaStream_t st = ctx->hstream[which];
         for (int k = 0; k < m; ++k) {
-            unsigned char *dy = ctx->stage_in[which] + in_frame * k;
-            unsigned char *duv = dy + in_y_pad;
-            TSVPP_CUDA(cudaMemcpyAsync(dy, frames[base + k].y, in_y, cudaMemcpyHostToDevice, st));
-            TSVPP_CUDA(cudaMemcpyAsync(duv, frames[base + k].uv, in_uv, cudaMemcpyHostToDevice, st));
             dframes[k] = frames[base + k];
-            dframes[k].y = dy;
-            dframes[k].uv = duv;
+            if (zero_copy) {
+                dframes[k].y = zy[base + k];
+                dframes[k].uv = zuv[base + k];
+            } else {
+                unsigned char *dy = ctx->stage_in[which] + in_frame * k;
+                unsigned char *duv = dy + in_y_pad;
+                TSVPP_CUDA(cudaMemcpyAsync(dy, frames[base + k].y, in_y, cudaMemcpyHostToDevice, st));
+                TSVPP_CUDA(cudaMemcpyAsync(duv, frames[base + k].uv, in_uv, cudaMemcpyHostToDevice, st));
+                dframes[k].y = dy;
+                dframes[k].uv = duv;
+            }
             douts[k] = ctx->stage_out[which] + out_frame * k;
         }
         rc = tsvpp_convert_batch(ctx, dframes.data(), m, p, douts.data(), st);
@@ -976,6 +1015,8 @@ int tsvpp_debug_pow23(const double *w, int n, double *w2, double *w3) {
     cudaFree(d);
     return TSVPP_OK;
 }
+
+int tsvpp_last_host_path(const TsvppContext *ctx) { return ctx ? ctx->last_host_zero_copy : 0; }
 
 unsigned long long tsvpp_launch_count(const TsvppContext *ctx) { return ctx ? ctx->launches.load() : 0ull; }
 

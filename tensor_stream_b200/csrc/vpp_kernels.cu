@@ -197,11 +197,35 @@ __device__ __forceinline__ ItemCoord decode_item(const PlanDev &P, int item) {
     return c;
 }
 
+// Work items of one CTA advance by gridDim.x: keep (frame, strip, tile) as a mixed-radix counter
+// instead of dividing every iteration.
+struct ItemIter {
+    int frame, strip, tile;
+    int d_frame, d_strip, d_tile;
+    __device__ __forceinline__ void init(const PlanDev &P, int first, int step) {
+        const ItemCoord c = decode_item(P, first);
+        frame = c.frame; strip = c.strip; tile = c.tile;
+        d_tile = step % P.ntiles;
+        const int q = step / P.ntiles;
+        d_strip = q % P.nstrips;
+        d_frame = q / P.nstrips;
+    }
+    __device__ __forceinline__ void next(const PlanDev &P) {
+        tile += d_tile;
+        int carry = tile >= P.ntiles ? 1 : 0;
+        tile -= carry ? P.ntiles : 0;
+        strip += d_strip + carry;
+        carry = strip >= P.nstrips ? 1 : 0;
+        strip -= carry ? P.nstrips : 0;
+        frame += d_frame + carry;
+    }
+};
+
 // One bulk copy per (output row of the strip, vertical tap).
 template <bool NEED_UV>
-__device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDev *__restrict__ frames, int item,
-                                                 unsigned char *stage, uint64_t *bar, int lane, uint64_t policy) {
-    const ItemCoord ic = decode_item(P, item);
+__device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDev *__restrict__ frames,
+                                                 const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane,
+                                                 uint64_t policy) {
     const FrameDev fr = frames[ic.frame];
     const int nl = 2 * P.rp * P.K;            // luma slots
     const int nc = NEED_UV ? P.rp * P.K : 0;  // chroma slots
@@ -228,9 +252,8 @@ __device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDe
 // producer warp (correct for any alignment; bytes past the plane end read as 0), then a plain
 // mbarrier arrive.  Slow path by design: NVDEC surfaces and torch tensors take the bulk path.
 template <bool NEED_UV>
-__device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev *__restrict__ frames, int item,
-                                               unsigned char *stage, uint64_t *bar, int lane) {
-    const ItemCoord ic = decode_item(P, item);
+__device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev *__restrict__ frames,
+                                               const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane) {
     const FrameDev fr = frames[ic.frame];
     const int nl = 2 * P.rp * P.K;
     const int nc = NEED_UV ? P.rp * P.K : 0;
@@ -489,14 +512,21 @@ __global__ void __launch_bounds__(kMaxThreads, (RS == RS_BICUBIC || RS == RS_ARE
     if (warp == 0) {
         // ================= producer =================
         const uint64_t policy = l2_policy_evict_first();
-        for (int it = 0; it < my_items; ++it) {
-            const int s = it % NS;
-            mbar_wait(empty + s, (uint32_t)(((it / NS) & 1) ^ 1));  // stage free (passes at once the first round)
+        ItemIter ic;
+        ic.init(P, first, (int)gridDim.x);
+        int s = 0;
+        uint32_t phase = 1;  // a fresh "empty" barrier passes a wait on parity 1: every stage starts free
+        for (int it = 0; it < my_items; ++it, ic.next(P)) {
+            mbar_wait(empty + s, phase);
             unsigned char *stage = stages + (size_t)s * P.stage_bytes;
             if (BULK)
-                issue_stage_bulk<NEED_UV>(P, frames, first + it * gridDim.x, stage, full + s, lane, policy);
+                issue_stage_bulk<NEED_UV>(P, frames, ic, stage, full + s, lane, policy);
             else
-                fill_stage_ldg<NEED_UV>(P, frames, first + it * gridDim.x, stage, full + s, lane);
+                fill_stage_ldg<NEED_UV>(P, frames, ic, stage, full + s, lane);
+            if (++s == NS) {
+                s = 0;
+                phase ^= 1u;
+            }
         }
         return;
     }
@@ -514,10 +544,11 @@ __global__ void __launch_bounds__(kMaxThreads, (RS == RS_BICUBIC || RS == RS_ARE
     int cur_tile = -1;
     ColT l0, l1, c0, c1;  // column parameters (kept in registers when small)
 
-    for (int it = 0; it < my_items; ++it) {
-        const int item = first + it * gridDim.x;
-        const ItemCoord ic = decode_item(P, item);
-        const int s = it % NS;
+    ItemIter ic;
+    ic.init(P, first, (int)gridDim.x);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < my_items; ++it, ic.next(P)) {
         const unsigned char *stage = stages + (size_t)s * P.stage_bytes;
         const int colbase = ic.tile * P.tw + 2 * tx;
         const int i0 = (ic.strip * P.rp + ty) * 2;  // first output row of this thread's block
@@ -541,7 +572,7 @@ __global__ void __launch_bounds__(kMaxThreads, (RS == RS_BICUBIC || RS == RS_ARE
             }
         }
 
-        mbar_wait(full + s, (uint32_t)((it / NS) & 1));
+        mbar_wait(full + s, phase);
 
         int Yv[2][2] = {{0, 0}, {0, 0}};
         int U = 0, V = 0;
@@ -568,8 +599,18 @@ __global__ void __launch_bounds__(kMaxThreads, (RS == RS_BICUBIC || RS == RS_ARE
         // all shared-memory reads of this stage are done: hand it back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+        if (++s == NS) {
+            s = 0;
+            phase ^= 1u;
+        }
 
-        if (active && nx > 0 && ny > 0) emit2x2<OK>(P, frames[ic.frame].out, i0, j0, Yv, U, V, nx, ny, vec);
+        if (active && nx > 0 && ny > 0) {
+            void *outp = frames[ic.frame].out;
+            if (nx == 2 && ny == 2 && vec)
+                emit2x2<OK>(P, outp, i0, j0, Yv, U, V, 2, 2, true);  // constants fold: straight-line stores
+            else
+                emit2x2<OK>(P, outp, i0, j0, Yv, U, V, nx, ny, vec);
+        }
     }
 }
 

@@ -84,6 +84,8 @@ def load_library():
     L.tsvpp_convert_batch_host.argtypes = [vp, C.POINTER(TsvppFrame), C.c_int, C.POINTER(TsvppParams),
                                            C.POINTER(vp)]
     L.tsvpp_convert_batch_host.restype = C.c_int
+    L.tsvpp_last_host_path.argtypes = [vp]
+    L.tsvpp_last_host_path.restype = C.c_int
     L.tsvpp_launch_count.argtypes = [vp]
     L.tsvpp_launch_count.restype = C.c_ulonglong
     L.tsvpp_describe_plan.argtypes = [vp, C.POINTER(TsvppFrame), C.POINTER(TsvppParams), C.c_char_p, C.c_size_t]
@@ -212,6 +214,9 @@ class VideoProcessor:
         p = params.c
         _check(self._L.tsvpp_describe_plan(self._h, C.byref(f), C.byref(p), buf, 1024))
         return buf.value.decode()
+
+    def last_host_path(self):
+        return "zero-copy" if self._L.tsvpp_last_host_path(self._h) else "staged-h2d"
 
     def launch_count(self):
         return int(self._L.tsvpp_launch_count(self._h))

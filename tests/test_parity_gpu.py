@@ -272,6 +272,22 @@ def test_host_buffer_entry_matches(vp):
         assert _same(o.reshape(-1), _run_oracle(y, uv, kw))
 
 
+def test_host_buffer_entry_zero_copy_from_pinned_memory(vp):
+    """Pinned host frames are read in place by the kernel (zero-copy); pageable ones are staged.
+    Same bits either way."""
+    kw = SYNTH[0][4]
+    frames = [_synthetic(1920, 1080, seed=300 + i) for i in range(6)]
+    pinned = [(torch.from_numpy(y).pin_memory(), torch.from_numpy(uv).pin_memory()) for y, uv in frames]
+    outs = vp.convert_batch_host(pinned, _params(kw), 1920, 1080)
+    assert vp.last_host_path() == "zero-copy"
+    for (y, uv), o in zip(frames, outs):
+        assert _same(o.reshape(-1), _run_oracle(y, uv, kw))
+    outs = vp.convert_batch_host(frames, _params(kw), 1920, 1080)  # pageable numpy
+    assert vp.last_host_path() == "staged-h2d"
+    for (y, uv), o in zip(frames, outs):
+        assert _same(o.reshape(-1), _run_oracle(y, uv, kw))
+
+
 def test_exhaustive_yuv_to_rgb(vp):
     """All 2^24 (Y,U,V) triples through the no-resize colour path, bit-exact against the oracle's
     scalar conversion (contracted vs non-contracted evaluation differs for 248 values: A.1)."""
