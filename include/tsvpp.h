@@ -99,8 +99,9 @@ void tsvpp_batch_destroy(TsvppBatch *batch);
 int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
                              void *const *out);
 
-/* 1 if the last tsvpp_convert_batch_host() call read its inputs in place from pinned host memory
- * (zero-copy, only the needed source rows cross PCIe), 0 if it staged whole frames with H2D copies. */
+/* Bit 0: the last tsvpp_convert_batch_host() call read its inputs in place from pinned host memory
+ * (zero-copy, only the needed source rows cross PCIe) instead of staging whole frames with H2D
+ * copies.  Bit 1: it wrote the outputs straight into pinned host memory (no D2H copy). */
 int tsvpp_last_host_path(const TsvppContext *ctx);
 
 /* Counters for evidence: number of fused-kernel launches issued by this context so far. */

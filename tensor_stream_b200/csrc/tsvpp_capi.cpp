@@ -970,7 +970,36 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
         }
         (void)cudaGetLastError();
     }
-    ctx->last_host_zero_copy = zero_copy ? 1 : 0;
+    // Zero-copy output: pinned host output buffers are written by the kernel's own (coalesced,
+    // streaming) stores, full-duplex with the input reads -- no staging buffer, no D2H copy.
+    bool zc_out = env_int("TSVPP_HOST_ZEROCOPY_OUT", 1) != 0;
+    std::vector<void *> zout;
+    if (zc_out) {
+        zout.resize(n);
+        for (int i = 0; i < n; ++i) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, out[i]) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
+                zc_out = false;
+                break;
+            }
+            zout[i] = a.devicePointer;
+        }
+        (void)cudaGetLastError();
+    }
+    ctx->last_host_zero_copy = (zero_copy ? 1 : 0) | (zc_out ? 2 : 0);
+    if (zero_copy && zc_out) {
+        // nothing to stage on either side: one launch over the whole batch
+        std::vector<TsvppFrame> f(n);
+        for (int i = 0; i < n; ++i) {
+            f[i] = frames[i];
+            f[i].y = zy[i];
+            f[i].uv = zuv[i];
+        }
+        rc = tsvpp_convert_batch(ctx, f.data(), n, p, zout.data(), ctx->hstream[0]);
+        if (rc) return rc;
+        TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
+        return TSVPP_OK;
+    }
     std::vector<TsvppFrame> dframes(chunk);
     std::vector<void *> douts(chunk);
     int which = 0;
@@ -990,12 +1019,13 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
                 dframes[k].y = dy;
                 dframes[k].uv = duv;
             }
-            douts[k] = ctx->stage_out[which] + out_frame * k;
+            douts[k] = zc_out ? zout[base + k] : (void *)(ctx->stage_out[which] + out_frame * k);
         }
         rc = tsvpp_convert_batch(ctx, dframes.data(), m, p, douts.data(), st);
         if (rc) return rc;
-        for (int k = 0; k < m; ++k)
-            TSVPP_CUDA(cudaMemcpyAsync(out[base + k], douts[k], elems * es, cudaMemcpyDeviceToHost, st));
+        if (!zc_out)
+            for (int k = 0; k < m; ++k)
+                TSVPP_CUDA(cudaMemcpyAsync(out[base + k], douts[k], elems * es, cudaMemcpyDeviceToHost, st));
         // the staging buffers of this stream are reused two chunks later: the stream order
         // already serialises that, nothing to wait for on the host here
     }

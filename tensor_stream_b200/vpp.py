@@ -216,7 +216,10 @@ class VideoProcessor:
         return buf.value.decode()
 
     def last_host_path(self):
-        return "zero-copy" if self._L.tsvpp_last_host_path(self._h) else "staged-h2d"
+        """How the last convert_batch_host call moved data: inputs read in place ("zero-copy") or
+        staged with H2D copies; "+out" when the outputs were written straight to pinned host memory."""
+        m = self._L.tsvpp_last_host_path(self._h)
+        return ("zero-copy" if m & 1 else "staged-h2d") + ("+out" if m & 2 else "")
 
     def launch_count(self):
         return int(self._L.tsvpp_launch_count(self._h))

@@ -282,6 +282,11 @@ def test_host_buffer_entry_zero_copy_from_pinned_memory(vp):
     assert vp.last_host_path() == "zero-copy"
     for (y, uv), o in zip(frames, outs):
         assert _same(o.reshape(-1), _run_oracle(y, uv, kw))
+    pout = [torch.zeros((3, 256, 256), dtype=torch.float32).pin_memory() for _ in frames]
+    vp.convert_batch_host(pinned, _params(kw), 1920, 1080, pout)  # pinned in AND out: no copies at all
+    assert vp.last_host_path() == "zero-copy+out"
+    for (y, uv), o in zip(frames, pout):
+        assert _same(o.numpy().reshape(-1), _run_oracle(y, uv, kw))
     outs = vp.convert_batch_host(frames, _params(kw), 1920, 1080)  # pageable numpy
     assert vp.last_host_path() == "staged-h2d"
     for (y, uv), o in zip(frames, outs):
