@@ -347,7 +347,10 @@ def run_ours(args):
                         "output.  Both are inside the timed region; the call returns with the results in host memory"},
         "gpu_launches": int(launches) * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                     # ncu dram__bytes_read+write of this kernel, per frame (committed capture under
+                     # profiles/), scaled to this run's frames per launch
+                     "traffic": ((traffic or {}).get("dram_bytes_per_frame") or 0) * n or None,
+                     "traffic_source": (traffic or {}).get("source"),
                      "algorithmic_bytes_per_frame": B_FULL, "frames_per_launch": n,
                      "launch_ms_avg": avg_launch, "launch_ms_median": med_launch, "peak_source": peak_src,
                      "note": "achieved = frames_per_launch * B_full / launch time (CUDA events); the kernel fetches only "
