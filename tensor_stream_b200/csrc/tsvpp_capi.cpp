@@ -208,6 +208,16 @@ void bicubic_taps(int X, int diff, int len, int t[4]) {
     t[3] = X + 2 * d;
 }
 
+// all four weights multiples of 2^-12 with |c| <= 2: products with a byte and their partial sums
+// are then exact in float32 (<= 23 significant bits), so the f32 row sum equals the FP64 one
+int weights_exact(const double *c) {
+    for (int k = 0; k < 4; ++k) {
+        const double v = c[k] * 4096.0;
+        if (std::fabs(c[k]) > 2.0 || v != std::floor(v)) return 0;
+    }
+    return 1;
+}
+
 struct DeviceArena {
     std::vector<unsigned char> host;
     size_t add(const void *p, size_t bytes) {
@@ -545,12 +555,16 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             for (int k = 0; k < 4; ++k) {
                 cl[j].o[k] = rel(tap_l[(size_t)j * 4 + k], a0l[t]);
                 cl[j].c[k] = cxw[(size_t)4 * j + k];
+                cl[j].cf[k] = (float)cl[j].c[k];
             }
+            cl[j].exact = weights_exact(cl[j].c);
             if (need_uv && lo_c[j] >= 0) {
                 for (int k = 0; k < 4; ++k) {
                     cc[j].o[k] = rel(tap_c[(size_t)j * 4 + k], a0c[t]);
                     cc[j].c[k] = cxw[(size_t)4 * (j >> 1) + k];
+                    cc[j].cf[k] = (float)cc[j].c[k];
                 }
+                cc[j].exact = weights_exact(cc[j].c);
             }
         }
         off_col_l = ar.add(cl.data(), cl.size() * sizeof(ColBicubic));
@@ -577,6 +591,12 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     const size_t off_rsc = ar.add(rowsrc_c.data(), rowsrc_c.size() * sizeof(int));
     const size_t off_wy = ar.add(wy.data(), wy.size() * sizeof(float));
     const size_t off_cy = ar.add(cyw.data(), cyw.size() * sizeof(double));
+    std::vector<float> cyf(cyw.size());
+    std::vector<int> cy_exact(cyw.size() / 4 + 1, 0);
+    for (size_t i = 0; i < cyw.size(); ++i) cyf[i] = (float)cyw[i];
+    for (size_t r = 0; r + 3 < cyw.size(); r += 4) cy_exact[r / 4] = weights_exact(&cyw[r]);
+    const size_t off_cyf = ar.add(cyf.data(), cyf.size() * sizeof(float));
+    const size_t off_cye = ar.add(cy_exact.data(), cy_exact.size() * sizeof(int));
     const size_t off_px = ar.add(patx.data(), patx.size() * sizeof(float));
     const size_t off_py = ar.add(paty.data(), paty.size() * sizeof(float));
 
@@ -606,6 +626,8 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     D.col_c = base + off_col_c;
     D.wy = (const float *)(base + off_wy);
     D.cy = (const double *)(base + off_cy);
+    D.cyf = (const float *)(base + off_cyf);
+    D.cy_exact = (const int *)(base + off_cye);
     D.px = (const float *)(base + off_px);
     D.py = (const float *)(base + off_py);
 

@@ -120,6 +120,28 @@ __device__ __forceinline__ int bicubic_dot(const double c0, const double c1, con
     return b;
 }
 
+// The same row sum, evaluated in float32 first.  |s32 - s_real| < 2e-4 (weights rounded to f32:
+// 4 * 2^-25 * 2 * 255; four f32 roundings at magnitude < 1024), the FP64 chain is within 1e-12 of
+// s_real, so whenever frac(s32 + .5) is farther than 2^-9 from an integer, floor(s32 + .5) IS
+// round(s64).  Otherwise -- or never, when the weights are multiples of 2^-12 and the f32 sum is
+// exact, ties included -- fall back to the reference's FP64 chain.  Bit-exact by construction.
+__device__ __forceinline__ int bicubic_dot_fast(const float *cf, const double *cd, int exact, uint32_t d0, uint32_t d1,
+                                                uint32_t d2, uint32_t d3) {
+    float s = __fmul_rn(cf[1], u2f(d1));
+    s = __fmaf_rn(cf[0], u2f(d0), s);
+    s = __fmaf_rn(cf[2], u2f(d2), s);
+    s = __fmaf_rn(cf[3], u2f(d3), s);
+    const float t = __fadd_rn(s, 0.5f);
+    const int bits = trunc_bits(t);  // 2^23 + floor(t) for t >= 0; below 2^23 for t < 0 (clamps to 0)
+    if (!exact) {
+        const float frac = __fsub_rn(t, __fsub_rn(__int_as_float(bits), kMagic));
+        const float eps = 0.001953125f;  // 2^-9
+        if (t >= 0.0f && (frac < eps || frac > 1.0f - eps))
+            return bicubic_dot(cd[0], cd[1], cd[2], cd[3], (int)d0, (int)d1, (int)d2, (int)d3);
+    }
+    return (int)(min(max(bits, (int)kMagicBits), (int)kMagicBits + 255) & 0xFF);
+}
+
 // reference src/ColorConversion.cu:6-39 (NV12toRGB24Kernel); chroma terms are shared by the
 // pixels of a 2x2 block.  R=(int)fma(Y',1.164,fma(V,1.596,.5)) etc..
 struct ChromaTerms {
@@ -311,15 +333,17 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
         return bilinear_px(s0[col.o0], s0[col.o1], s1[col.o0], s1[col.o1], col.w, wy);
     } else if constexpr (RS == RS_BICUBIC) {
         const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
-        const double c0 = col.c[0], c1 = col.c[1], c2 = col.c[2], c3 = col.c[3];
-        int b[4];
+        const float cf[4] = {col.cf[0], col.cf[1], col.cf[2], col.cf[3]};
+        const int exact_x = col.exact;
+        uint32_t b[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned char *s = slots + k * P.slot_stride;
-            b[k] = bicubic_dot(c0, c1, c2, c3, s[o0], s[o1], s[o2], s[o3]);
+            b[k] = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
         }
-        const double *cy = P.cy + (size_t)orow * 4;
-        return bicubic_dot(__ldg(cy + 0), __ldg(cy + 1), __ldg(cy + 2), __ldg(cy + 3), b[0], b[1], b[2], b[3]);
+        const float4 cyf4 = __ldg(reinterpret_cast<const float4 *>(P.cyf) + orow);
+        const float cyf[4] = {cyf4.x, cyf4.y, cyf4.z, cyf4.w};
+        return bicubic_dot_fast(cyf, P.cy + (size_t)orow * 4, __ldg(P.cy_exact + orow), b[0], b[1], b[2], b[3]);
     } else {
         // reference src/Resize.cu:160-178 (calculateAreaInterpolation): rows outer, columns
         // inner; w = px*py; div += w; sum = fma(d, w, sum); (int)(sum/div)

@@ -39,7 +39,9 @@ constexpr int kMaxStages = 8;       // mbarrier ring depth upper bound
 // column parameters, one per output sample column (luma: per output x; chroma: per chroma byte)
 struct ColNearest { int o; };                                  // smem byte offset inside a slot
 struct ColBilinear { int o0, o1; float w; int pad; };          // taps at o0 / o1, weight of o1
-struct ColBicubic { int o[4]; double c[4]; };                  // Keys a=-0.75 taps and weights
+// Keys a=-0.75 taps; c = the reference's FP64 weights, cf = the same rounded to f32, exact = all four
+// are multiples of 2^-12 (then the f32 evaluation of a row sum is exact, ties included)
+struct ColBicubic { int o[4]; double c[4]; float cf[4]; int exact; int pad; };
 struct ColArea { int o; int prow; };                           // first tap, pattern row index
 
 struct FrameDev {
@@ -76,6 +78,8 @@ struct PlanDev {
     const void *col_c;      // [ntiles*tw] Col* for chroma bytes
     const float *wy;        // [nstrips*2*rp] bilinear vertical weight per output row index
     const double *cy;       // [nstrips*2*rp][4] bicubic vertical weights per output row index
+    const float *cyf;       // same, rounded to f32
+    const int *cy_exact;    // [nstrips*2*rp] 1 if the row's four weights are multiples of 2^-12
     const float *px;        // [PX][KX] AREA horizontal pattern
     const float *py;        // [PY][K]  AREA vertical pattern
 };

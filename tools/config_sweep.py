@@ -80,6 +80,9 @@ def main():
             for norm, fc, pl in ((False, vpp.FourCC.RGB24, vpp.Planes.MERGED), (True, vpp.FourCC.BGR24, vpp.Planes.PLANAR)):
                 if (dw, dh) == (1920, 1080) and rt != vpp.ResizeType.NEAREST:
                     continue  # same size: no resize kernel runs whatever the type
+                name = "1080p->%dx%d %s %s" % (dw, dh, rt.name.lower(), "bgr planar f32" if norm else "rgb merged u8")
+                if os.environ.get("CS_ONLY") and os.environ["CS_ONLY"] not in name:
+                    continue
                 fp = vpp.FrameParameters(dw, dh, resize_type=rt, pixel_format=fc, planes_pos=pl, normalization=norm)
                 nfr = 160 if dw * dh <= 1024 * 1024 else (48 if dw * dh <= 1920 * 1080 else 16)
                 fps, outb = time_ours(v, ys[:nfr], uvs[:nfr], fp, W, H, 10)
@@ -87,8 +90,7 @@ def main():
                 plan = v.describe_plan(ys[0], uvs[0], fp)
                 keep = " ".join(x for x in plan.split() if x.split("=")[0] in ("tw", "rp", "K", "nstages", "ctas_per_sm"))
                 kw = dict(dst=(dw, dh), resize_type=rt.value, fourcc=fc.value, planes=pl.value, normalization=norm)
-                rfps = time_ref(ref, ys, uvs, W, H, kw, 1.0) if ref else float("nan")
-                name = "1080p->%dx%d %s %s" % (dw, dh, rt.name.lower(), "bgr planar f32" if norm else "rgb merged u8")
+                rfps = time_ref(ref, ys, uvs, W, H, kw, 1.0) if (ref and not os.environ.get("CS_NOREF")) else float("nan")
                 print("| %s | %.0f | %.0f | %.2f | %s | %.0f | %.0fx |" % (name, fps, fps * bfull / 1e9, fps * bfull / 1e9 / PEAK, keep, rfps, fps / rfps), flush=True)
     # C3: 3840x2160 NV12, crop (0,0,1920,1080) -> RGB24 merged 1280x720 bicubic uint8
     W, H = 3840, 2160
@@ -101,7 +103,7 @@ def main():
     plan = v.describe_plan(ys[0], uvs[0], fp)
     keep = " ".join(x for x in plan.split() if x.split("=")[0] in ("tw", "rp", "K", "nstages", "ctas_per_sm"))
     kw = dict(crop=(0, 0, 1920, 1080), dst=(1280, 720), resize_type=2, fourcc=1, planes=1, normalization=False)
-    rfps = time_ref(ref, ys, uvs, W, H, kw, 2.0) if ref else float("nan")
+    rfps = time_ref(ref, ys, uvs, W, H, kw, 2.0) if (ref and not os.environ.get("CS_NOREF")) else float("nan")
     print("| C3 4K crop 1080p->1280x720 bicubic rgb merged u8 | %.0f | %.0f | %.2f | %s | %.0f | %.0fx |" % (fps, fps * bfull / 1e9, fps * bfull / 1e9 / PEAK, keep, rfps, fps / rfps))
 
 
