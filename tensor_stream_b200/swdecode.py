@@ -196,3 +196,25 @@ def av_crc32(buf):
     b = bytes(buf)
     tab = L["avutil"].av_crc_get_table(3)
     return L["avutil"].av_crc(tab, 0xFFFFFFFF, b, len(b))
+
+
+def sws_nv12_to_rgb24(y, uv, dst_w=None, dst_h=None, bgr=False, flags=2):
+    """FFmpeg swscale NV12 -> RGB24/BGR24 (uint8, merged), the CPU baseline BASELINE.md names
+    (R-CPU).  flags: SWS_BILINEAR=2 (| SWS_FULL_CHR_H_INT=0x2000 | SWS_ACCURATE_RND=0x40000)."""
+    L = load_ffmpeg()
+    sws = L["swscale"]
+    h, w = y.shape
+    dst_w, dst_h = dst_w or w, dst_h or h
+    ctx = sws.sws_getContext(w, h, 23, dst_w, dst_h, 3 if bgr else 2, flags, None, None, None)
+    if not ctx:
+        raise RuntimeError("sws_getContext failed")
+    y = np.ascontiguousarray(y)
+    uv = np.ascontiguousarray(uv)
+    dst = np.empty((dst_h, dst_w, 3), dtype=np.uint8)
+    src = (C.c_void_p * 4)(y.ctypes.data, uv.ctypes.data, None, None)
+    sst = (C.c_int * 4)(y.strides[0], uv.strides[0], 0, 0)
+    dp = (C.c_void_p * 4)(dst.ctypes.data, None, None, None)
+    dst_st = (C.c_int * 4)(dst_w * 3, 0, 0, 0)
+    sws.sws_scale(ctx, src, sst, 0, h, dp, dst_st)
+    sws.sws_freeContext(ctx)
+    return dst

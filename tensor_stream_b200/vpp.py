@@ -302,6 +302,18 @@ class VideoProcessor:
         return out_np
 
 
+def convert_batch_aten(frames, params, widths=None):
+    """Same result as VideoProcessor.convert_batch, through the PyTorch C++ extension
+    (csrc/aten_handoff.cpp): outputs are at::empty tensors from torch's caching allocator, the
+    launch goes to torch's current stream, no Python-side pointer juggling."""
+    from . import aten_build
+    mod = aten_build.load()
+    w, h = widths if widths is not None else (0, 0)
+    return mod.convert_batch([f[0] for f in frames], [f[1] for f in frames], w, h, list(params.crop_coords),
+                             params.width, params.height, params.resize_type.value, params.pixel_format.value,
+                             params.planes_pos.value, params.normalization)
+
+
 def _host_ptr(a):
     if hasattr(a, "data_ptr"):
         return a.data_ptr()

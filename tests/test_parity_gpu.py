@@ -293,6 +293,43 @@ def test_host_buffer_entry_zero_copy_from_pinned_memory(vp):
         assert _same(o.reshape(-1), _run_oracle(y, uv, kw))
 
 
+def test_aten_handoff_extension_matches_ctypes_path(vp):
+    """csrc/aten_handoff.cpp (the PyTorch C++ extension of the hand-off): same bits
+    as the ctypes path, outputs allocated by torch on torch's current stream."""
+    from tensor_stream_b200 import aten_build, vpp
+    if aten_build.so_path() is None:
+        pytest.skip("_tsvpp_torch.so not built")
+    for kw in (SYNTH[0][4], dict(dst=(320, 240), resize_type=G.BICUBIC, fourcc=G.RGB24),
+               dict(crop=(64, 32, 704, 512), fourcc=G.HSV), dict(fourcc=G.UYVY, dst=(320, 240))):
+        frames = [_synthetic(1280, 720, seed=400 + i) for i in range(3)]
+        dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
+        a = vpp.convert_batch_aten(dev, _params(kw))
+        b = vp.convert_batch(dev, _params(kw))
+        torch.cuda.synchronize()
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and x.dtype == y.dtype and torch.equal(x, y)
+
+
+def test_tensor_stream_converter_read_readme_call(vp):
+    """The README's flagship call of the reference (README.md:20-27) through the facade with a
+    synthetic decoded-frame source: (3,256,256) float32 on cuda:0, equal to the oracle."""
+    from oracle import oracle as O
+    from tensor_stream_b200 import FourCC, Planes, ResizeType, TensorStreamConverter
+    reader = TensorStreamConverter("synthetic://1920x1080", cuda_device=0)
+    reader.initialize()
+    reader.start()
+    t, idx = reader.read(pixel_format=FourCC.BGR24, width=256, height=256, normalization=True,
+                         planes_pos=Planes.PLANAR, resize_type=ResizeType.BILINEAR, return_index=True)
+    assert tuple(t.shape) == (3, 256, 256) and t.dtype == torch.float32 and t.is_cuda and idx == 1
+    # regenerate frame 0 of the synthetic source and check against the oracle
+    from tensor_stream_b200.stream import SyntheticSource
+    y, uv = SyntheticSource(1920, 1080, torch.device("cuda", 0)).next_frame()
+    want = O.convert(y.cpu().numpy(), uv.cpu().numpy(), dst=(256, 256), resize_type=O.BILINEAR, fourcc=O.BGR24,
+                     planes=O.PLANAR, normalization=True)[0]
+    assert _same(t.cpu().numpy().reshape(-1), want)
+    reader.stop()
+
+
 def test_exhaustive_yuv_to_rgb(vp):
     """All 2^24 (Y,U,V) triples through the no-resize colour path, bit-exact against the oracle's
     scalar conversion (contracted vs non-contracted evaluation differs for 248 values: A.1)."""

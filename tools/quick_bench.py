@@ -14,6 +14,10 @@ def main():
     n = int(os.environ.get("QB_FRAMES", "160"))
     iters = int(os.environ.get("QB_ITERS", "20"))
     W, H = 1920, 1080
+    cfg = os.environ.get("QB_CFG", "c2")
+    if cfg == "c3":
+        W, H = 3840, 2160
+        n = min(n, 40)
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
@@ -22,6 +26,12 @@ def main():
     v = vpp.VideoProcessor(0)
     cfgs = [("C2 bilinear 256 bgr planar f32", vpp.FrameParameters(256, 256, resize_type=vpp.ResizeType.BILINEAR,
              pixel_format=vpp.FourCC.BGR24, planes_pos=vpp.Planes.PLANAR, normalization=True))]
+    if cfg == "c3":
+        cfgs = [("C3 4K crop 1080p -> 1280x720 bicubic rgb merged u8", vpp.FrameParameters(
+            1280, 720, crop_coords=(0, 0, 1920, 1080), resize_type=vpp.ResizeType.BICUBIC))]
+    elif cfg == "area":
+        cfgs = [("area 256 bgr planar f32", vpp.FrameParameters(256, 256, resize_type=vpp.ResizeType.AREA,
+                 pixel_format=vpp.FourCC.BGR24, planes_pos=vpp.Planes.PLANAR, normalization=True))]
     if os.environ.get("QB_ALL"):
         for rt in vpp.ResizeType:
             cfgs.append(("%s 256 rgb merged u8" % rt.name, vpp.FrameParameters(256, 256, resize_type=rt)))
@@ -41,7 +51,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         fps = n / (ms * 1e-3)
-        bfull = W * H * 1.5 + int(np.prod(shape)) * es
+        sw, sh = (1920, 1080) if cfg == "c3" else (W, H)
+        bfull = sw * sh * 1.5 + int(np.prod(shape)) * es
         print("  %.3f ms / %d frames -> %.0f fps, B_full %.1f GB/s" % (ms, n, fps, fps * bfull / 1e9))
         b.destroy()
 
