@@ -397,9 +397,15 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     int tw = 32, rp = 1, nstages = 1, ntiles = 1, slot_stride = 16;
     std::vector<int> a0l, lenl, a0c, lenc;
     bool found = false;
-    for (int cand_rp = std::min(2, std::max(1, want_rp)); cand_rp >= 1 && !found; --cand_rp) {
+    // Scored search over (row pairs per strip, tile width, ring depth): maximise the number of
+    // consumer threads resident per SM (occupancy hides the stage latency -- profiles/r1_v*_sweep),
+    // then prefer wider tiles (fewer, longer bulk copies) and a deeper ring.
+    const int reg_ctas = (rs == RS_NEAREST || rs == RS_BILINEAR) ? 4 : (rs == RS_AREA ? 3 : 2);  // __launch_bounds__
+    long best_score = -1;
+    for (int cand_rp = 2; cand_rp >= 1; --cand_rp) {
         if (cand_rp == 2 && dh < 4) continue;
-        for (int cand = 256; cand >= 32 && !found; cand >>= 1) {
+        if (env_int("TSVPP_RP", 0) && cand_rp != want_rp) continue;
+        for (int cand = 256; cand >= 32; cand >>= 1) {
             if (cand > want_tw) continue;
             if (cand > 32 && cand >= 2 * round_up(dw, 32)) continue;  // don't over-size tiles for narrow outputs
             const int nt = (dw + cand - 1) / cand;
@@ -434,28 +440,27 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             const int nslots = (need_uv ? 3 : 2) * cand_rp * K;
             const size_t stage = (size_t)nslots * stride;
             const size_t fixed = 2 * 8 * kMaxStages + 128;
-            int ns = 0;
-            {
-                const size_t budgets[3] = {56 * 1024, 110 * 1024, smem_cap};
-                for (size_t bgt : budgets) {
-                    if (bgt > smem_cap) bgt = smem_cap;
-                    if (bgt < fixed + stage) continue;
-                    const int n = (int)((bgt - fixed) / stage);
-                    if (n >= 2 || (bgt == smem_cap && n >= 1)) {
-                        ns = std::min(n, want_ns > 0 ? want_ns : 4);
-                        ns = std::min(ns, kMaxStages);
-                        break;
-                    }
+            const int consumers = (cand / 2) * cand_rp;
+            const int threads = 32 + round_up(consumers, 32);
+            for (int ns = (want_ns > 0 ? want_ns : 4); ns >= 1; --ns) {
+                if (want_ns > 0 && ns != want_ns) continue;
+                const size_t smem = fixed + stage * ns;
+                if (smem > smem_cap) continue;
+                // 1 KB per CTA is reserved by the driver; 228 KB per SM
+                const int by_smem = (int)((size_t)(228 * 1024) / (smem + 1024));
+                const int ctas = std::max(1, std::min(std::min(by_smem, reg_ctas), 2048 / threads));
+                // one stage can only be refilled while another is consumed: a single stage serialises
+                const long score = (long)ctas * consumers * (ns >= 2 ? 8 : 1) * 64 + (cand / 32) * 4 + std::min(ns, 3);
+                if (score > best_score) {
+                    best_score = score;
+                    found = true;
+                    tw = cand;
+                    rp = cand_rp;
+                    nstages = ns;
+                    ntiles = nt;
+                    slot_stride = stride;
+                    a0l = A0l; lenl = Ll; a0c = A0c; lenc = Lc;
                 }
-            }
-            if (ns >= 1) {
-                found = true;
-                tw = cand;
-                rp = cand_rp;
-                nstages = ns;
-                ntiles = nt;
-                slot_stride = stride;
-                a0l = A0l; lenl = Ll; a0c = A0c; lenc = Lc;
             }
         }
     }

@@ -29,6 +29,8 @@ def main():
     if cfg == "c3":
         cfgs = [("C3 4K crop 1080p -> 1280x720 bicubic rgb merged u8", vpp.FrameParameters(
             1280, 720, crop_coords=(0, 0, 1920, 1080), resize_type=vpp.ResizeType.BICUBIC))]
+    elif cfg == "noresize":
+        cfgs = [("1080p NV12 -> RGB24 merged u8, native size (the reference's default read())", vpp.FrameParameters())]
     elif cfg == "area":
         cfgs = [("area 256 bgr planar f32", vpp.FrameParameters(256, 256, resize_type=vpp.ResizeType.AREA,
                  pixel_format=vpp.FourCC.BGR24, planes_pos=vpp.Planes.PLANAR, normalization=True))]
