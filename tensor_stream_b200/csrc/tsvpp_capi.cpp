@@ -400,7 +400,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     // Scored search over (row pairs per strip, tile width, ring depth): maximise the number of
     // consumer threads resident per SM (occupancy hides the stage latency -- profiles/r1_v*_sweep),
     // then prefer wider tiles (fewer, longer bulk copies) and a deeper ring.
-    const int reg_ctas = (rs == RS_NEAREST || rs == RS_BILINEAR) ? 4 : (rs == RS_AREA ? 3 : 2);  // __launch_bounds__
+    const int reg_ctas = (rs == RS_NEAREST || rs == RS_BILINEAR) ? 4 : 3;  // __launch_bounds__
     long best_score = -1;
     for (int cand_rp = 2; cand_rp >= 1; --cand_rp) {
         if (cand_rp == 2 && dh < 4) continue;

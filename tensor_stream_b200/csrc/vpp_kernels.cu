@@ -505,7 +505,7 @@ __device__ __forceinline__ void emit2x2(const PlanDev &P, void *outp, int i0, in
 // The fused kernel.  blockDim.x = 32 (producer warp) + round_up(tw/2 * rp, 32) consumers.
 // ---------------------------------------------------------------------------------------
 template <int RS, int OK, bool BULK>
-__global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 2 : (RS == RS_AREA ? 3 : 4)) vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
+__global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 3 : (RS == RS_AREA ? 3 : 4)) vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
                                                                 int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     using ColT = typename ColOf<RS>::T;
