@@ -400,7 +400,12 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     // Scored search over (row pairs per strip, tile width, ring depth): maximise the number of
     // consumer threads resident per SM (occupancy hides the stage latency -- profiles/r1_v*_sweep),
     // then prefer wider tiles (fewer, longer bulk copies) and a deeper ring.
-    const int reg_ctas = (rs == RS_NEAREST || rs == RS_BILINEAR) ? 4 : 3;  // __launch_bounds__
+    // columns per consumer thread: 4 (float4 / uchar4 stores, half the per-item overhead per pixel)
+    // for wide outputs of the light resamplers, else 2
+    int bw = (fused_supports_bw4(rs) && dw % 4 == 0 && dw >= 512) ? 4 : 2;
+    if (env_int("TSVPP_BW", 0) == 2) bw = 2;
+    if (env_int("TSVPP_BW", 0) == 4 && fused_supports_bw4(rs) && dw % 4 == 0) bw = 4;
+    const int regs_assumed = bw == 4 ? 80 : ((rs == RS_NEAREST || rs == RS_BILINEAR) ? 56 : 72);  // caps implied by __launch_bounds__
     long best_score = -1;
     for (int cand_rp = 2; cand_rp >= 1; --cand_rp) {
         if (cand_rp == 2 && dh < 4) continue;
@@ -440,8 +445,9 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             const int nslots = (need_uv ? 3 : 2) * cand_rp * K;
             const size_t stage = (size_t)nslots * stride;
             const size_t fixed = 2 * 8 * kMaxStages + 128;
-            const int consumers = (cand / 2) * cand_rp;
+            const int consumers = (cand / bw) * cand_rp;
             const int threads = 32 + round_up(consumers, 32);
+            const int reg_ctas = std::max(1, 65536 / (threads * regs_assumed));
             for (int ns = (want_ns > 0 ? want_ns : 4); ns >= 1; --ns) {
                 if (want_ns > 0 && ns != want_ns) continue;
                 const size_t smem = fixed + stage * ns;
@@ -611,7 +617,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
 
     PlanDev &D = pl->dev;
     D.dw = dw; D.dh = dh; D.cw2 = cw2; D.ch2 = ch2;
-    D.tw = tw; D.ntiles = ntiles; D.nstrips = nstrips; D.rp = rp;
+    D.tw = tw; D.ntiles = ntiles; D.nstrips = nstrips; D.rp = rp; D.bw = bw;
     D.K = K; D.KX = KX;
     D.slot_stride = slot_stride;
     D.stage_bytes = (need_uv ? 3 : 2) * rp * K * slot_stride;
@@ -641,16 +647,16 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     pl->bulk = bulk;
     pl->smem = fused_smem_bytes(D);
     if (pl->smem > smem_cap) return TSVPP_UNSUPPORTED;
-    int rc = configure_fused(rs, ok, bulk, smem_cap);
+    int rc = configure_fused(rs, ok, bulk, bw, smem_cap);
     if (rc) return rc;
-    pl->ctas_per_sm = std::max(1, max_ctas_per_sm(rs, ok, bulk, fused_block_threads(D), pl->smem));
+    pl->ctas_per_sm = std::max(1, max_ctas_per_sm(rs, ok, bulk, bw, fused_block_threads(D), pl->smem));
     const int cap_ctas = env_int("TSVPP_CTAS_PER_SM", 0);
     if (cap_ctas > 0) pl->ctas_per_sm = std::min(pl->ctas_per_sm, cap_ctas);
     pl->out_w = dw;
     pl->out_h = dh;
     pl->out_elems = (size_t)(channels_of(p.fourcc) * dw * dh);
     pl->elem_size = (p.normalization || p.fourcc == TSVPP_HSV) ? 4 : 1;
-    pl->vec_ok_geom = (dw % 2 == 0) ? 1 : 0;
+    pl->vec_ok_geom = (dw % bw == 0) ? 1 : 0;
     // bytes one frame's work items fetch from the source planes (what crosses HBM / PCIe)
     long fetch = 0;
     for (int t = 0; t < ntiles; ++t)
@@ -659,9 +665,9 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     char buf[640];
     static const char *rs_names[] = {"nearest", "bilinear", "bicubic", "area"};
     std::snprintf(buf, sizeof(buf),
-                  "resample=%s out_kind=%d fill=%s tw=%d rp=%d K=%d KX=%d ntiles=%d nstrips=%d slot_stride=%d "
+                  "resample=%s out_kind=%d fill=%s bw=%d tw=%d rp=%d K=%d KX=%d ntiles=%d nstrips=%d slot_stride=%d "
                   "stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d crop=%d resize=%d fetch_bytes_per_frame=%ld",
-                  rs_names[rs], ok, bulk ? "bulk" : "ldg", tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
+                  rs_names[rs], ok, bulk ? "bulk" : "ldg", bw, tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
                   nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize, fetch);
     pl->desc = buf;
     out = std::move(pl);

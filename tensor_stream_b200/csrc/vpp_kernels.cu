@@ -364,137 +364,171 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
 }
 
 // ---------------------------------------------------------------------------------------
-// Colour conversion + layout for one 2x2 block of output pixels
+// Colour conversion + layout for one block of 2 rows x BW columns (BW = 2 or 4) per thread
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void st2f(float *p, float a, float b, bool vec, int nx) {
-    if (vec && nx == 2) {
-        __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b));
+// NW consecutive 32-bit words to `p`; AW = guaranteed alignment of p in words (1, 2 or 4).
+template <int NW, int AW>
+__device__ __forceinline__ void st_words(void *p, const uint32_t (&w)[NW]) {
+    if constexpr (AW >= 4 && NW % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < NW; k += 4)
+            __stcs(reinterpret_cast<uint4 *>(p) + k / 4, make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]));
+    } else if constexpr (AW >= 2 && NW % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < NW; k += 2) __stcs(reinterpret_cast<uint2 *>(p) + k / 2, make_uint2(w[k], w[k + 1]));
     } else {
-        p[0] = a;
-        if (nx == 2) p[1] = b;
-    }
-}
-__device__ __forceinline__ void st2b(unsigned char *p, uint32_t a, uint32_t b, bool vec, int nx) {
-    if (vec && nx == 2) {
-        *reinterpret_cast<unsigned short *>(p) = (unsigned short)(a | (b << 8));
-    } else {
-        p[0] = (unsigned char)a;
-        if (nx == 2) p[1] = (unsigned char)b;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) __stcs(reinterpret_cast<unsigned int *>(p) + k, w[k]);
     }
 }
 
-// Y[a][b]: resized luma of pixel (i0+a, j0+b); U,V: the block's chroma sample (0 if it does not
-// exist).  nx, ny: how many columns/rows of the block lie inside the image.
-template <int OK>
-__device__ __forceinline__ void emit2x2(const PlanDev &P, void *outp, int i0, int j0, const int (&Yv)[2][2], int U, int V,
-                                        int nx, int ny, bool vec) {
+// one row segment of NE float elements (NE = BW or 3*BW)
+template <int NE, int BW>
+__device__ __forceinline__ void st_row_f32(float *dst, const float (&e)[NE], bool full, int nvalid) {
+    if (full) {
+        uint32_t w[NE];
+#pragma unroll
+        for (int k = 0; k < NE; ++k) w[k] = __float_as_uint(e[k]);
+        st_words<NE, BW>(dst, w);  // alignment: BW floats (8 or 16 bytes) by construction
+    } else {
+        for (int k = 0; k < nvalid; ++k) dst[k] = e[k];
+    }
+}
+// one row segment of NE byte elements (values 0..255 in uint32)
+template <int NE, int BW>
+__device__ __forceinline__ void st_row_u8(unsigned char *dst, const uint32_t (&e)[NE], bool full, int nvalid) {
+    if (full) {
+        if constexpr (NE % 4 == 0) {
+            uint32_t w[NE / 4];
+#pragma unroll
+            for (int k = 0; k < NE / 4; ++k)
+                w[k] = e[4 * k] | (e[4 * k + 1] << 8) | (e[4 * k + 2] << 16) | (e[4 * k + 3] << 24);
+            st_words<NE / 4, 1>(dst, w);
+        } else {  // NE == 2 or 6: 16-bit stores
+#pragma unroll
+            for (int k = 0; k < NE / 2; ++k)
+                *reinterpret_cast<unsigned short *>(dst + 2 * k) = (unsigned short)(e[2 * k] | (e[2 * k + 1] << 8));
+        }
+    } else {
+        for (int k = 0; k < nvalid; ++k) dst[k] = (unsigned char)e[k];
+    }
+}
+
+// Yv[a][b]: resized luma of pixel (i0+a, j0+b); UV[p] = {U,V} of column pair p (0 if it does not
+// exist).  nx, ny: how many columns/rows of the block lie inside the image; full: nx==BW && ny==2
+// and the vector-store alignment conditions hold.
+template <int OK, int BW>
+__device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0, int j0, const int (&Yv)[2][BW],
+                                           const int (&UV)[BW / 2][2], int nx, int ny, bool full) {
     const int dw = P.dw, dh = P.dh;
-    if constexpr (OK == OUT_Y800_U8) {
-        for (int a = 0; a < ny; ++a)
-            st2b((unsigned char *)outp + (size_t)(i0 + a) * dw + j0, Yv[a][0], Yv[a][1], vec, nx);
-    } else if constexpr (OK == OUT_Y800_F32) {
-        for (int a = 0; a < ny; ++a)
-            st2f((float *)outp + (size_t)(i0 + a) * dw + j0, div255_u8(Yv[a][0]), div255_u8(Yv[a][1]), vec, nx);
-    } else if constexpr (OK == OUT_NV12_U8 || OK == OUT_NV12_F32) {
-        // reference src/ColorConversion.cu:211-233 (NV12MergeBuffers): Y plane then UV plane
-        const size_t wh = (size_t)dw * dh;
-        const bool has_uv = ((i0 >> 1) < P.ch2) && ((j0 >> 1) < P.cw2);
+    const int nrow = full ? 2 : ny;
+    if constexpr (OK == OUT_Y800_U8 || OK == OUT_NV12_U8) {
+        unsigned char *o = (unsigned char *)outp;
+        for (int a = 0; a < nrow; ++a) {
+            uint32_t e[BW];
+#pragma unroll
+            for (int b = 0; b < BW; ++b) e[b] = (uint32_t)Yv[a][b];
+            st_row_u8<BW, BW>(o + (size_t)(i0 + a) * dw + j0, e, full, nx);
+        }
         if constexpr (OK == OUT_NV12_U8) {
-            unsigned char *o = (unsigned char *)outp;
-            for (int a = 0; a < ny; ++a) st2b(o + (size_t)(i0 + a) * dw + j0, Yv[a][0], Yv[a][1], vec, nx);
-            if (has_uv) st2b(o + wh + (size_t)(i0 >> 1) * dw + j0, U, V, vec, 2);
-        } else {
-            float *o = (float *)outp;
-            for (int a = 0; a < ny; ++a)
-                st2f(o + (size_t)(i0 + a) * dw + j0, div255_u8(Yv[a][0]), div255_u8(Yv[a][1]), vec, nx);
-            if (has_uv) st2f(o + wh + (size_t)(i0 >> 1) * dw + j0, div255_u8(U), div255_u8(V), vec, 2);
+            // reference src/ColorConversion.cu:211-233 (NV12MergeBuffers): Y plane then UV plane
+            if ((i0 >> 1) < P.ch2) {
+                uint32_t e[BW];
+#pragma unroll
+                for (int p = 0; p < BW / 2; ++p) { e[2 * p] = (uint32_t)UV[p][0]; e[2 * p + 1] = (uint32_t)UV[p][1]; }
+                const int nuv = 2 * max(0, min(BW / 2, P.cw2 - (j0 >> 1)));
+                st_row_u8<BW, BW>(o + (size_t)dw * dh + (size_t)(i0 >> 1) * dw + j0, e, full && nuv == BW, nuv);
+            }
+        }
+    } else if constexpr (OK == OUT_Y800_F32 || OK == OUT_NV12_F32) {
+        float *o = (float *)outp;
+        for (int a = 0; a < nrow; ++a) {
+            float e[BW];
+#pragma unroll
+            for (int b = 0; b < BW; ++b) e[b] = div255_u8((uint32_t)Yv[a][b]);
+            st_row_f32<BW, BW>(o + (size_t)(i0 + a) * dw + j0, e, full, nx);
+        }
+        if constexpr (OK == OUT_NV12_F32) {
+            if ((i0 >> 1) < P.ch2) {
+                float e[BW];
+#pragma unroll
+                for (int p = 0; p < BW / 2; ++p) { e[2 * p] = div255_u8((uint32_t)UV[p][0]); e[2 * p + 1] = div255_u8((uint32_t)UV[p][1]); }
+                const int nuv = 2 * max(0, min(BW / 2, P.cw2 - (j0 >> 1)));
+                st_row_f32<BW, BW>(o + (size_t)dw * dh + (size_t)(i0 >> 1) * dw + j0, e, full && nuv == BW, nuv);
+            }
         }
     } else {
-        // RGB family
-        const ChromaTerms t = chroma_terms(U, V);
-        int R[2][2], G[2][2], B[2][2];
+        // RGB family: channel values as magic bit patterns, [row][col][channel]
+        int C[2][BW][3];
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) yuv_px_bits(Yv[a][b], t, R[a][b], G[a][b], B[a][b]);
-
-        if constexpr (OK == OUT_HSV_F32) {
-            // reference src/ColorConversion.cu:360-372: from normalised RGB (never BGR), merged
-            for (int a = 0; a < ny; ++a) {
-                float h[2][3];
-#pragma unroll
-                for (int b = 0; b < 2; ++b)
-                    rgb_to_hsv(div255_bits(R[a][b]), div255_bits(G[a][b]), div255_bits(B[a][b]), h[b][0], h[b][1], h[b][2]);
-                float *o = (float *)outp + ((size_t)(i0 + a) * dw + j0) * 3;
-                if (vec && nx == 2) {
-                    __stcs(reinterpret_cast<float2 *>(o), make_float2(h[0][0], h[0][1]));
-                    __stcs(reinterpret_cast<float2 *>(o) + 1, make_float2(h[0][2], h[1][0]));
-                    __stcs(reinterpret_cast<float2 *>(o) + 2, make_float2(h[1][1], h[1][2]));
-                } else {
-                    for (int b = 0; b < nx; ++b) {
-                        o[3 * b] = h[b][0];
-                        o[3 * b + 1] = h[b][1];
-                        o[3 * b + 2] = h[b][2];
-                    }
-                }
-            }
-            return;
-        }
-        if (P.swap_rb) {  // BGR (ColorConversion.cu:304-305): first channel is B
+        for (int p = 0; p < BW / 2; ++p) {
+            const ChromaTerms t = chroma_terms(UV[p][0], UV[p][1]);
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const int tmp = R[a][b];
-                    R[a][b] = B[a][b];
-                    B[a][b] = tmp;
+                for (int b = 0; b < 2; ++b) yuv_px_bits(Yv[a][2 * p + b], t, C[a][2 * p + b][0], C[a][2 * p + b][1], C[a][2 * p + b][2]);
+        }
+        if constexpr (OK == OUT_HSV_F32) {
+            // reference src/ColorConversion.cu:360-372: from normalised RGB (never BGR), merged
+            for (int a = 0; a < nrow; ++a) {
+                float e[3 * BW];
+#pragma unroll
+                for (int b = 0; b < BW; ++b)
+                    rgb_to_hsv(div255_bits(C[a][b][0]), div255_bits(C[a][b][1]), div255_bits(C[a][b][2]), e[3 * b], e[3 * b + 1], e[3 * b + 2]);
+                st_row_f32<3 * BW, BW>((float *)outp + ((size_t)(i0 + a) * dw + j0) * 3, e, full, 3 * nx);
+            }
+            return;
+        }
+        if (P.swap_rb) {  // BGR: first channel is B (ColorConversion.cu:304-305)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < BW; ++b) {
+                    const int tmp = C[a][b][0];
+                    C[a][b][0] = C[a][b][2];
+                    C[a][b][2] = tmp;
                 }
         }
-        if constexpr (OK == OUT_RGB_PLANAR_F32) {
+        if constexpr (OK == OUT_RGB_PLANAR_F32 || OK == OUT_RGB_PLANAR_U8) {
             const size_t plane = (size_t)dw * dh;
-            for (int a = 0; a < ny; ++a) {
-                float *o = (float *)outp + (size_t)(i0 + a) * dw + j0;
-                st2f(o, div255_bits(R[a][0]), div255_bits(R[a][1]), vec, nx);
-                st2f(o + plane, div255_bits(G[a][0]), div255_bits(G[a][1]), vec, nx);
-                st2f(o + 2 * plane, div255_bits(B[a][0]), div255_bits(B[a][1]), vec, nx);
-            }
-        } else if constexpr (OK == OUT_RGB_PLANAR_U8) {
-            const size_t plane = (size_t)dw * dh;
-            for (int a = 0; a < ny; ++a) {
-                unsigned char *o = (unsigned char *)outp + (size_t)(i0 + a) * dw + j0;
-                st2b(o, bits_u8(R[a][0]), bits_u8(R[a][1]), vec, nx);
-                st2b(o + plane, bits_u8(G[a][0]), bits_u8(G[a][1]), vec, nx);
-                st2b(o + 2 * plane, bits_u8(B[a][0]), bits_u8(B[a][1]), vec, nx);
-            }
-        } else if constexpr (OK == OUT_RGB_MERGED_F32) {
-            for (int a = 0; a < ny; ++a) {
-                float *o = (float *)outp + ((size_t)(i0 + a) * dw + j0) * 3;
-                if (vec && nx == 2) {
-                    __stcs(reinterpret_cast<float2 *>(o), make_float2(div255_bits(R[a][0]), div255_bits(G[a][0])));
-                    __stcs(reinterpret_cast<float2 *>(o) + 1, make_float2(div255_bits(B[a][0]), div255_bits(R[a][1])));
-                    __stcs(reinterpret_cast<float2 *>(o) + 2, make_float2(div255_bits(G[a][1]), div255_bits(B[a][1])));
-                } else {
-                    for (int b = 0; b < nx; ++b) {
-                        o[3 * b] = div255_bits(R[a][b]);
-                        o[3 * b + 1] = div255_bits(G[a][b]);
-                        o[3 * b + 2] = div255_bits(B[a][b]);
+            for (int a = 0; a < nrow; ++a) {
+                const size_t off = (size_t)(i0 + a) * dw + j0;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    if constexpr (OK == OUT_RGB_PLANAR_F32) {
+                        float e[BW];
+#pragma unroll
+                        for (int b = 0; b < BW; ++b) e[b] = div255_bits(C[a][b][ch]);
+                        st_row_f32<BW, BW>((float *)outp + ch * plane + off, e, full, nx);
+                    } else {
+                        uint32_t e[BW];
+#pragma unroll
+                        for (int b = 0; b < BW; ++b) e[b] = bits_u8(C[a][b][ch]);
+                        st_row_u8<BW, BW>((unsigned char *)outp + ch * plane + off, e, full, nx);
                     }
                 }
             }
-        } else if constexpr (OK == OUT_RGB_MERGED_U8) {
-            for (int a = 0; a < ny; ++a) {
-                unsigned char *o = (unsigned char *)outp + ((size_t)(i0 + a) * dw + j0) * 3;
-                if (vec && nx == 2) {
-                    unsigned short *o2 = reinterpret_cast<unsigned short *>(o);
-                    o2[0] = (unsigned short)(bits_u8(R[a][0]) | (bits_u8(G[a][0]) << 8));
-                    o2[1] = (unsigned short)(bits_u8(B[a][0]) | (bits_u8(R[a][1]) << 8));
-                    o2[2] = (unsigned short)(bits_u8(G[a][1]) | (bits_u8(B[a][1]) << 8));
-                } else {
-                    for (int b = 0; b < nx; ++b) {
-                        o[3 * b] = (unsigned char)bits_u8(R[a][b]);
-                        o[3 * b + 1] = (unsigned char)bits_u8(G[a][b]);
-                        o[3 * b + 2] = (unsigned char)bits_u8(B[a][b]);
+        } else {
+            for (int a = 0; a < nrow; ++a) {
+                const size_t off = ((size_t)(i0 + a) * dw + j0) * 3;
+                if constexpr (OK == OUT_RGB_MERGED_F32) {
+                    float e[3 * BW];
+#pragma unroll
+                    for (int b = 0; b < BW; ++b) {
+                        e[3 * b] = div255_bits(C[a][b][0]);
+                        e[3 * b + 1] = div255_bits(C[a][b][1]);
+                        e[3 * b + 2] = div255_bits(C[a][b][2]);
                     }
+                    st_row_f32<3 * BW, BW>((float *)outp + off, e, full, 3 * nx);
+                } else {
+                    uint32_t e[3 * BW];
+#pragma unroll
+                    for (int b = 0; b < BW; ++b) {
+                        e[3 * b] = bits_u8(C[a][b][0]);
+                        e[3 * b + 1] = bits_u8(C[a][b][1]);
+                        e[3 * b + 2] = bits_u8(C[a][b][2]);
+                    }
+                    st_row_u8<3 * BW, BW>((unsigned char *)outp + off, e, full, 3 * nx);
                 }
             }
         }
@@ -502,11 +536,12 @@ __device__ __forceinline__ void emit2x2(const PlanDev &P, void *outp, int i0, in
 }
 
 // ---------------------------------------------------------------------------------------
-// The fused kernel.  blockDim.x = 32 (producer warp) + round_up(tw/2 * rp, 32) consumers.
+// The fused kernel.  blockDim.x = 32 (producer warp) + round_up(tw/BW * rp, 32) consumers;
+// every consumer thread owns a block of 2 rows x BW columns of the output.
 // ---------------------------------------------------------------------------------------
-template <int RS, int OK, bool BULK>
-__global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 3 : (RS == RS_AREA ? 3 : 4)) vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
-                                                                int nframes, int vec_ok) {
+template <int RS, int OK, bool BULK, int BW>
+__global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((RS == RS_BICUBIC || RS == RS_AREA) ? 3 : 4))
+    vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     using ColT = typename ColOf<RS>::T;
     constexpr bool SMALL_COL = sizeof(ColT) <= 16;
@@ -557,16 +592,16 @@ __global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 3 : (RS == RS_
 
     // ================= consumers =================
     const int ctid = tid - 32;
-    const int half_tw = P.tw >> 1;
-    const int tx = ctid % half_tw;  // column pair inside the tile
-    const int ty = ctid / half_tw;  // row pair inside the strip
+    const int blocks_x = P.tw / BW;
+    const int tx = ctid % blocks_x;  // column block inside the tile
+    const int ty = ctid / blocks_x;  // row pair inside the strip
     const bool active = ty < P.rp;
     const bool vec = vec_ok != 0;
     const ColT *col_l = reinterpret_cast<const ColT *>(P.col_l);
     const ColT *col_c = reinterpret_cast<const ColT *>(P.col_c);
 
     int cur_tile = -1;
-    ColT l0, l1, c0, c1;  // column parameters (kept in registers when small)
+    ColT lreg[BW], creg[BW];  // column parameters (kept in registers when small)
 
     ItemIter ic;
     ic.init(P, first, (int)gridDim.x);
@@ -574,18 +609,17 @@ __global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 3 : (RS == RS_
     uint32_t phase = 0;
     for (int it = 0; it < my_items; ++it, ic.next(P)) {
         const unsigned char *stage = stages + (size_t)s * P.stage_bytes;
-        const int colbase = ic.tile * P.tw + 2 * tx;
+        const int colbase = ic.tile * P.tw + BW * tx;
         const int i0 = (ic.strip * P.rp + ty) * 2;  // first output row of this thread's block
         const int ci = ic.strip * P.rp + ty;        // its chroma row
         const int j0 = colbase;                     // first output column
         float wy0 = 0.f, wy1 = 0.f, wyc = 0.f;
         if (active) {
             if (SMALL_COL && ic.tile != cur_tile) {
-                l0 = col_l[colbase];
-                l1 = col_l[colbase + 1];
-                if (NEED_UV) {
-                    c0 = col_c[colbase];
-                    c1 = col_c[colbase + 1];
+#pragma unroll
+                for (int b = 0; b < BW; ++b) {
+                    lreg[b] = col_l[colbase + b];
+                    if (NEED_UV) creg[b] = col_c[colbase + b];
                 }
                 cur_tile = ic.tile;
             }
@@ -598,26 +632,36 @@ __global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 3 : (RS == RS_
 
         mbar_wait(full + s, phase);
 
-        int Yv[2][2] = {{0, 0}, {0, 0}};
-        int U = 0, V = 0;
-        const int nx = min(2, P.dw - j0), ny = min(2, P.dh - i0);
-        if (active && nx > 0 && ny > 0) {
+        int Yv[2][BW];
+        int UV[BW / 2][2];
+#pragma unroll
+        for (int b = 0; b < BW; ++b) Yv[0][b] = Yv[1][b] = 0;
+#pragma unroll
+        for (int p = 0; p < BW / 2; ++p) UV[p][0] = UV[p][1] = 0;
+        const int nx = min(BW, P.dw - j0), ny = min(2, P.dh - i0);
+        const bool work = active && nx > 0 && ny > 0;
+        if (work) {
             const unsigned char *sl0 = stage + (size_t)((2 * ty) * P.K) * P.slot_stride;
             const unsigned char *sl1 = sl0 + (size_t)P.K * P.slot_stride;
-            const ColT &L0 = SMALL_COL ? l0 : col_l[colbase];
-            const ColT &L1 = SMALL_COL ? l1 : col_l[colbase + 1];
-            Yv[0][0] = resample<RS>(P, sl0, L0, i0, 1, wy0);
-            if (nx > 1) Yv[0][1] = resample<RS>(P, sl0, L1, i0, 1, wy0);
-            if (ny > 1) {
-                Yv[1][0] = resample<RS>(P, sl1, L0, i0 + 1, 1, wy1);
-                if (nx > 1) Yv[1][1] = resample<RS>(P, sl1, L1, i0 + 1, 1, wy1);
+#pragma unroll
+            for (int b = 0; b < BW; ++b) {
+                if (b < nx) {
+                    const ColT &L = SMALL_COL ? lreg[b] : col_l[colbase + b];
+                    Yv[0][b] = resample<RS>(P, sl0, L, i0, 1, wy0);
+                    if (ny > 1) Yv[1][b] = resample<RS>(P, sl1, L, i0 + 1, 1, wy1);
+                }
             }
-            if (NEED_UV && ci < P.ch2 && (j0 >> 1) < P.cw2) {
+            if (NEED_UV && ci < P.ch2) {
                 const unsigned char *sc = stage + (size_t)((2 * P.rp + ty) * P.K) * P.slot_stride;
-                const ColT &C0 = SMALL_COL ? c0 : col_c[colbase];
-                const ColT &C1 = SMALL_COL ? c1 : col_c[colbase + 1];
-                U = resample<RS>(P, sc, C0, ci, 2, wyc);
-                V = resample<RS>(P, sc, C1, ci, 2, wyc);
+#pragma unroll
+                for (int p = 0; p < BW / 2; ++p) {
+                    if ((j0 >> 1) + p < P.cw2) {
+                        const ColT &C0 = SMALL_COL ? creg[2 * p] : col_c[colbase + 2 * p];
+                        const ColT &C1 = SMALL_COL ? creg[2 * p + 1] : col_c[colbase + 2 * p + 1];
+                        UV[p][0] = resample<RS>(P, sc, C0, ci, 2, wyc);
+                        UV[p][1] = resample<RS>(P, sc, C1, ci, 2, wyc);
+                    }
+                }
             }
         }
         // all shared-memory reads of this stage are done: hand it back to the producer
@@ -628,12 +672,12 @@ __global__ void __launch_bounds__(kMaxThreads, RS == RS_BICUBIC ? 3 : (RS == RS_
             phase ^= 1u;
         }
 
-        if (active && nx > 0 && ny > 0) {
+        if (work) {
             void *outp = frames[ic.frame].out;
-            if (nx == 2 && ny == 2 && vec)
-                emit2x2<OK>(P, outp, i0, j0, Yv, U, V, 2, 2, true);  // constants fold: straight-line stores
+            if (nx == BW && ny == 2 && vec)
+                emit_block<OK, BW>(P, outp, i0, j0, Yv, UV, BW, 2, true);  // constants fold: straight-line vector stores
             else
-                emit2x2<OK>(P, outp, i0, j0, Yv, U, V, nx, ny, vec);
+                emit_block<OK, BW>(P, outp, i0, j0, Yv, UV, nx, ny, false);
         }
     }
 }
@@ -678,36 +722,43 @@ void launch_bicubic_weights(const double *w_dev, double *c_dev, int n, cudaStrea
 using KernelFn = void (*)(const PlanDev, const FrameDev *, int, int);
 
 template <int RS, int OK>
-static KernelFn pick_fill(bool bulk) {
-    return bulk ? vpp_fused_kernel<RS, OK, true> : vpp_fused_kernel<RS, OK, false>;
+static KernelFn pick_fill(bool bulk, int bw) {
+    // 4-column blocks only where they pay (wide outputs of the light resamplers); the bicubic and
+    // area instantiations are tap-bound, not store-bound
+    if constexpr (RS == RS_NEAREST || RS == RS_BILINEAR) {
+        if (bw == 4) return bulk ? vpp_fused_kernel<RS, OK, true, 4> : vpp_fused_kernel<RS, OK, false, 4>;
+    }
+    return bulk ? vpp_fused_kernel<RS, OK, true, 2> : vpp_fused_kernel<RS, OK, false, 2>;
 }
 template <int RS>
-static KernelFn pick_out(int ok, bool bulk) {
+static KernelFn pick_out(int ok, bool bulk, int bw) {
     switch (ok) {
-        case OUT_RGB_PLANAR_U8: return pick_fill<RS, OUT_RGB_PLANAR_U8>(bulk);
-        case OUT_RGB_PLANAR_F32: return pick_fill<RS, OUT_RGB_PLANAR_F32>(bulk);
-        case OUT_RGB_MERGED_U8: return pick_fill<RS, OUT_RGB_MERGED_U8>(bulk);
-        case OUT_RGB_MERGED_F32: return pick_fill<RS, OUT_RGB_MERGED_F32>(bulk);
-        case OUT_Y800_U8: return pick_fill<RS, OUT_Y800_U8>(bulk);
-        case OUT_Y800_F32: return pick_fill<RS, OUT_Y800_F32>(bulk);
-        case OUT_HSV_F32: return pick_fill<RS, OUT_HSV_F32>(bulk);
-        case OUT_NV12_U8: return pick_fill<RS, OUT_NV12_U8>(bulk);
-        case OUT_NV12_F32: return pick_fill<RS, OUT_NV12_F32>(bulk);
+        case OUT_RGB_PLANAR_U8: return pick_fill<RS, OUT_RGB_PLANAR_U8>(bulk, bw);
+        case OUT_RGB_PLANAR_F32: return pick_fill<RS, OUT_RGB_PLANAR_F32>(bulk, bw);
+        case OUT_RGB_MERGED_U8: return pick_fill<RS, OUT_RGB_MERGED_U8>(bulk, bw);
+        case OUT_RGB_MERGED_F32: return pick_fill<RS, OUT_RGB_MERGED_F32>(bulk, bw);
+        case OUT_Y800_U8: return pick_fill<RS, OUT_Y800_U8>(bulk, bw);
+        case OUT_Y800_F32: return pick_fill<RS, OUT_Y800_F32>(bulk, bw);
+        case OUT_HSV_F32: return pick_fill<RS, OUT_HSV_F32>(bulk, bw);
+        case OUT_NV12_U8: return pick_fill<RS, OUT_NV12_U8>(bulk, bw);
+        case OUT_NV12_F32: return pick_fill<RS, OUT_NV12_F32>(bulk, bw);
     }
     return nullptr;
 }
-static KernelFn pick_kernel(int rs, int ok, bool bulk) {
+static KernelFn pick_kernel(int rs, int ok, bool bulk, int bw) {
     switch (rs) {
-        case RS_NEAREST: return pick_out<RS_NEAREST>(ok, bulk);
-        case RS_BILINEAR: return pick_out<RS_BILINEAR>(ok, bulk);
-        case RS_BICUBIC: return pick_out<RS_BICUBIC>(ok, bulk);
-        case RS_AREA: return pick_out<RS_AREA>(ok, bulk);
+        case RS_NEAREST: return pick_out<RS_NEAREST>(ok, bulk, bw);
+        case RS_BILINEAR: return pick_out<RS_BILINEAR>(ok, bulk, bw);
+        case RS_BICUBIC: return pick_out<RS_BICUBIC>(ok, bulk, bw);
+        case RS_AREA: return pick_out<RS_AREA>(ok, bulk, bw);
     }
     return nullptr;
 }
 
+bool fused_supports_bw4(int rs) { return rs == RS_NEAREST || rs == RS_BILINEAR; }
+
 int fused_block_threads(const PlanDev &P) {
-    const int cons = (P.tw / 2) * P.rp;
+    const int cons = (P.tw / P.bw) * P.rp;
     return 32 + (cons + 31) / 32 * 32;
 }
 
@@ -717,15 +768,15 @@ size_t fused_smem_bytes(const PlanDev &P) {
 
 // the dynamic-shared-memory opt-in is a per-FUNCTION attribute shared by every plan that uses
 // the instantiation: always raise it to the device maximum
-int configure_fused(int rs, int ok, bool bulk, size_t smem_optin_max) {
-    KernelFn fn = pick_kernel(rs, ok, bulk);
+int configure_fused(int rs, int ok, bool bulk, int bw, size_t smem_optin_max) {
+    KernelFn fn = pick_kernel(rs, ok, bulk, bw);
     if (!fn) return (int)cudaErrorMissingConfiguration;  // reference ColorConversion.cu:376
     return (int)cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_optin_max);
 }
 
-int max_ctas_per_sm(int rs, int ok, bool bulk, int threads, size_t smem_bytes) {
-    KernelFn fn = pick_kernel(rs, ok, bulk);
+int max_ctas_per_sm(int rs, int ok, bool bulk, int bw, int threads, size_t smem_bytes) {
+    KernelFn fn = pick_kernel(rs, ok, bulk, bw);
     if (!fn) return 0;
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reinterpret_cast<const void *>(fn), threads, smem_bytes) !=
@@ -738,7 +789,7 @@ int max_ctas_per_sm(int rs, int ok, bool bulk, int threads, size_t smem_bytes) {
 
 int launch_fused(int rs, int ok, bool bulk, const PlanDev &P, const FrameDev *frames_dev, int nframes, int vec_ok,
                  int grid, size_t smem_bytes, cudaStream_t stream) {
-    KernelFn fn = pick_kernel(rs, ok, bulk);
+    KernelFn fn = pick_kernel(rs, ok, bulk, P.bw);
     if (!fn) return (int)cudaErrorMissingConfiguration;
     fn<<<grid, fused_block_threads(P), smem_bytes, stream>>>(P, frames_dev, nframes, vec_ok);
     return (int)cudaGetLastError();

@@ -10,8 +10,9 @@ namespace tsvpp {
 
 int fused_block_threads(const PlanDev &P);
 size_t fused_smem_bytes(const PlanDev &P);
-int configure_fused(int rs, int ok, bool bulk, size_t smem_optin_max);
-int max_ctas_per_sm(int rs, int ok, bool bulk, int threads, size_t smem_bytes);
+bool fused_supports_bw4(int rs);
+int configure_fused(int rs, int ok, bool bulk, int bw, size_t smem_optin_max);
+int max_ctas_per_sm(int rs, int ok, bool bulk, int bw, int threads, size_t smem_bytes);
 int launch_fused(int rs, int ok, bool bulk, const PlanDev &P, const FrameDev *frames_dev, int nframes, int vec_ok,
                  int grid, size_t smem_bytes, cudaStream_t stream);
 int launch_packed_yuv(int yuv444, int is_float, const FrameDev *frames_dev, int nframes, int w, int h, int pitch,

@@ -57,6 +57,7 @@ struct PlanDev {
     int tw;                 // tile width in output columns (32..256, multiple of 32)
     int ntiles, nstrips;    // work items per frame = nstrips * ntiles
     int rp;                 // row pairs per strip (1 or 2): a strip is 2*rp luma rows, rp chroma rows
+    int bw;                 // output columns per consumer thread (2 or 4); a thread owns 2 rows x bw columns
     int K;                  // vertical taps = slots per output row
     int KX;                 // horizontal taps (AREA only)
     int slot_stride;        // bytes between slots (multiple of 16)
