@@ -31,6 +31,9 @@ def main():
             1280, 720, crop_coords=(0, 0, 1920, 1080), resize_type=vpp.ResizeType.BICUBIC))]
     elif cfg == "noresize":
         cfgs = [("1080p NV12 -> RGB24 merged u8, native size (the reference's default read())", vpp.FrameParameters())]
+    elif cfg == "bil4k":
+        cfgs = [("1080p -> 3840x2160 bilinear bgr planar f32", vpp.FrameParameters(3840, 2160, resize_type=vpp.ResizeType.BILINEAR,
+                 pixel_format=vpp.FourCC.BGR24, planes_pos=vpp.Planes.PLANAR, normalization=True))]
     elif cfg == "area":
         cfgs = [("area 256 bgr planar f32", vpp.FrameParameters(256, 256, resize_type=vpp.ResizeType.AREA,
                  pixel_format=vpp.FourCC.BGR24, planes_pos=vpp.Planes.PLANAR, normalization=True))]
