@@ -402,7 +402,9 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     // then prefer wider tiles (fewer, longer bulk copies) and a deeper ring.
     // columns per consumer thread: 4 (float4 / uchar4 stores, half the per-item overhead per pixel)
     // for wide outputs of the light resamplers, else 2
-    int bw = (fused_supports_bw4(rs) && dw % 4 == 0 && dw >= 512) ? 4 : 2;
+    // (measured, profiles/r1_v5_*: +20-30 % for nearest / colour-only at >= 512 columns, +10-15 % for
+    // bilinear downscales, but -35 % for bilinear upscales, which are latency- not store-bound)
+    int bw = (fused_supports_bw4(rs) && dw % 4 == 0 && dw >= 512 && (rs == RS_NEAREST || (xr >= 1.0f && yr >= 1.0f))) ? 4 : 2;
     if (env_int("TSVPP_BW", 0) == 2) bw = 2;
     if (env_int("TSVPP_BW", 0) == 4 && fused_supports_bw4(rs) && dw % 4 == 0) bw = 4;
     const int regs_assumed = bw == 4 ? 80 : ((rs == RS_NEAREST || rs == RS_BILINEAR) ? 56 : 72);  // caps implied by __launch_bounds__
