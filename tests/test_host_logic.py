@@ -163,3 +163,30 @@ def test_two_rank_layout_over_gloo():
         assert p.exitcode == 0
     assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5, 7]
     assert res[0][2] == res[1][2] == [15.0, 100.0]
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly, not fall back, when there is no CUDA device."""
+    import torch
+    from tensor_stream_b200 import vpp
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        vpp.VideoProcessor(0)
+    h = C.c_void_p()
+    assert vpp.load_library().tsvpp_create(0, C.byref(h)) != 0  # a cudaError_t, no context
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under tensor_stream_b200/ or include/ may refer to it."""
+    bad = []
+    for base in ("tensor_stream_b200", "include"):
+        for root, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in root.split(os.sep):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cpp", ".h")):
+                    txt = open(os.path.join(root, f), errors="ignore").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle|liboracle|vpp_oracle\.h", txt, re.M):
+                        bad.append(os.path.join(root, f))
+    assert not bad, bad

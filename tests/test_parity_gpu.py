@@ -349,3 +349,33 @@ def test_exhaustive_yuv_to_rgb(vp):
     got = _run_cuda(vp, Y, UV, kw)
     want = _run_oracle(Y, UV, kw)
     assert _same(got, want), _diff_report(got, want)
+
+
+def test_error_codes_match_the_reference_contract(vp):
+    """Status codes of the boundary: 0, the reference's Internal enum, or a positive cudaError_t
+    (include/Common.h:19-24, src/ColorConversion.cu:376)."""
+    import ctypes as C
+    from tensor_stream_b200 import vpp
+    L = vpp.load_library()
+    y = torch.zeros((64, 64), dtype=torch.uint8, device="cuda")
+    uv = torch.zeros((32, 64), dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64 * 64 * 3, dtype=torch.uint8, device="cuda")
+    f = (vpp.TsvppFrame * 2)(vpp.TsvppFrame(y.data_ptr(), uv.data_ptr(), 64, 64, 64, 64),
+                             vpp.TsvppFrame(y.data_ptr(), uv.data_ptr(), 64, 64, 32, 32))
+    outs = (C.c_void_p * 2)(out.data_ptr(), out.data_ptr())
+    p = vpp.FrameParameters().c
+    assert L.tsvpp_convert_batch(vp._h, f, 0, C.byref(p), outs, None) == -3          # empty batch: VREADER_ERROR
+    assert L.tsvpp_convert_batch(vp._h, f, 2, C.byref(p), outs, None) == -2          # ragged batch: VREADER_UNSUPPORTED
+    p.fourcc = 42
+    assert L.tsvpp_convert_batch(vp._h, f, 1, C.byref(p), outs, None) == 52          # cudaErrorMissingConfiguration
+    p = vpp.FrameParameters().c
+    p.resize_type = 9
+    p.dst_width, p.dst_height = 32, 32
+    assert L.tsvpp_convert_batch(vp._h, f, 1, C.byref(p), outs, None) == -2
+    # an oversize crop is ignored, exactly like the reference (VideoProcessor.cpp:109)
+    big = vpp.FrameParameters(crop_coords=(0, 0, 640, 640))
+    o = vp.convert(y, uv, big)
+    assert tuple(o.shape) == (64, 64, 3)
+    with pytest.raises(vpp.VppError) as ei:
+        vp.convert(y, uv, vpp.FrameParameters(pixel_format=1), width=0, height=0)
+    assert str(ei.value) in ("-3", "1")
