@@ -85,7 +85,15 @@ constexpr uint32_t kMagicBits = 0x4B000000u;  // 2^23 as float bits
 constexpr float kMagic = 8388608.0f;
 
 // (float)b for 0 <= b < 2^23, exact
-__device__ __forceinline__ float u2f(uint32_t b) { return __fsub_rn(__uint_as_float(kMagicBits | b), kMagic); }
+__device__ __forceinline__ float u2f(uint32_t b) {
+#ifdef TSVPP_U2F_CVT
+    float f;  // 32-bit integer source: I2FP.F32.U32 (not the XU-pipe byte/short I2F forms)
+    asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(b));
+    return f;
+#else
+    return __fsub_rn(__uint_as_float(kMagicBits | b), kMagic);
+#endif
+}
 // bits of (2^23 + trunc(v)) for |v| < 2^22: (int)v == bits - kMagicBits when v >= 0; any negative
 // v yields bits < kMagicBits (only ever used before a clamp at 0)
 __device__ __forceinline__ int trunc_bits(float v) { return __float_as_int(__fadd_rz(v, kMagic)); }

@@ -59,10 +59,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIBPATH):
+    path = os.environ.get("TSVPP_LIB", _LIBPATH)  # developer override (A/B builds)
+    if not os.path.exists(path):
         raise ImportError("native library %s is missing: run `python -m tensor_stream_b200.build` "
-                          "(there is no CPU fallback)" % _LIBPATH)
-    L = C.CDLL(_LIBPATH)
+                          "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
     vp = C.c_void_p
     L.tsvpp_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.tsvpp_create.restype = C.c_int
