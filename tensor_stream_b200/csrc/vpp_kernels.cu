@@ -18,8 +18,9 @@
 //                   through uint8 exactly where the reference stores its NV12 intermediate,
 //                   then converted (BT.601), normalised and stored with vector stores.
 //                   No block-wide barrier anywhere in the steady state.
-// uint8 <-> float conversions use the 2^23 magic-number form (LOP/FADD, full-rate pipes) instead
-// of I2F/F2I (quarter-rate XU pipe): ncu showed XU as the busiest pipe of the first version.
+// uint8 -> float uses cvt.rn.f32.u32 on 32-bit registers (I2FP, full rate) and float -> uint8 the
+// 2^23 magic-number form (FADD.RZ + LOP) instead of the byte-typed I2F/F2I forms (quarter-rate XU
+// pipe): ncu showed XU as the busiest pipe of the first version.
 // Bit-exactness contract: see oracle/vpp_oracle.c (same formulas, same citations).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -86,12 +87,15 @@ constexpr float kMagic = 8388608.0f;
 
 // (float)b for 0 <= b < 2^23, exact
 __device__ __forceinline__ float u2f(uint32_t b) {
-#ifdef TSVPP_U2F_CVT
-    float f;  // 32-bit integer source: I2FP.F32.U32 (not the XU-pipe byte/short I2F forms)
+#ifdef TSVPP_U2F_MAGIC
+    return __fsub_rn(__uint_as_float(kMagicBits | b), kMagic);
+#else
+    // cvt on a 32-bit register compiles to I2FP.F32.U32 (one full-rate instruction); the u8/u16
+    // forms the compiler picks for (float)uchar are the quarter-rate XU-pipe I2F the first version
+    // was bound by.  Measured equal-or-faster than the 2-instruction magic form (A/B, round 1).
+    float f;
     asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(b));
     return f;
-#else
-    return __fsub_rn(__uint_as_float(kMagicBits | b), kMagic);
 #endif
 }
 // bits of (2^23 + trunc(v)) for |v| < 2^22: (int)v == bits - kMagicBits when v >= 0; any negative
