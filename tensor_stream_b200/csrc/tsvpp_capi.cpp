@@ -262,7 +262,7 @@ struct TsvppContext {
     std::map<PlanKey, std::unique_ptr<Plan>> plans;
     std::atomic<unsigned long long> launches{0};
     // descriptor ring for tsvpp_convert_batch (pinned host + device), guarded by events
-    static constexpr int kRing = 8;
+    static constexpr int kRing = 32;  // concurrent convert calls in flight (the reference allows maxConsumers = 5 by default)
     FrameDev *ring_host[kRing] = {};
     FrameDev *ring_dev[kRing] = {};
     cudaEvent_t ring_ev[kRing] = {};

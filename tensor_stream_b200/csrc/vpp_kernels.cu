@@ -282,9 +282,34 @@ __device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDe
     }
 }
 
-// Fallback fill for frames whose base/pitch are not 16-byte aligned: guarded byte loads by the
-// producer warp (correct for any alignment; bytes past the plane end read as 0), then a plain
-// mbarrier arrive.  Slow path by design: NVDEC surfaces and torch tensors take the bulk path.
+// Fallback fill for frames whose base/pitch are not 16-byte aligned: the producer warp copies each
+// row segment with aligned 32-bit global loads + funnel shifts (any source alignment; bytes outside
+// the plane read as 0), then a plain mbarrier arrive.  Slower than the TMA path by design: NVDEC
+// surfaces and torch tensors with 16-byte-multiple pitches take the bulk path.
+__device__ __forceinline__ uint32_t ld_word_guarded(const unsigned char *plane, long off, long plane_bytes) {
+    // the 4 bytes plane[off .. off+3]; `plane + off` is 4-byte aligned
+    if (off >= 0 && off + 4 <= plane_bytes) return __ldg(reinterpret_cast<const uint32_t *>(plane + off));
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long o = off + k;
+        if (o >= 0 && o < plane_bytes) v |= (uint32_t)__ldg(plane + o) << (8 * k);
+    }
+    return v;
+}
+__device__ __forceinline__ void copy_row_ldg(unsigned char *dst, const unsigned char *plane, long base, int len,
+                                             long plane_bytes, int lane) {
+    const int mis = (int)((reinterpret_cast<uintptr_t>(plane) + (uintptr_t)base) & 3);
+    const long abase = base - mis;  // 4-byte aligned address relative to the plane pointer
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    const int nwords = len >> 2;
+    for (int k = lane; k < nwords; k += 32) {
+        const uint32_t lo = ld_word_guarded(plane, abase + 4L * k, plane_bytes);
+        const uint32_t hi = mis ? ld_word_guarded(plane, abase + 4L * k + 4, plane_bytes) : 0u;
+        d32[k] = __funnelshift_r(lo, hi, mis * 8);
+    }
+}
+
 template <bool NEED_UV>
 __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev *__restrict__ frames,
                                                const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane) {
@@ -293,25 +318,14 @@ __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev 
     const int nc = NEED_UV ? P.rp * P.K : 0;
     const int a0l = P.seg_a0_l[ic.tile], lenl = P.seg_len_l[ic.tile];
     const int *rs_l = P.rowsrc_l + (size_t)ic.strip * nl;
-    for (int c = 0; c < nl; ++c) {
-        const long base = (long)rs_l[c] * P.pitch_y + a0l;
-        unsigned char *dst = stage + (size_t)c * P.slot_stride;
-        for (int b = lane; b < lenl; b += 32) {
-            const long g = base + b;
-            dst[b] = (g < P.plane_bytes_y) ? __ldg(fr.y + g) : (unsigned char)0;
-        }
-    }
+    for (int c = 0; c < nl; ++c)
+        copy_row_ldg(stage + (size_t)c * P.slot_stride, fr.y, (long)rs_l[c] * P.pitch_y + a0l, lenl, P.plane_bytes_y, lane);
     if (NEED_UV) {
         const int a0c = P.seg_a0_c[ic.tile], lenc = P.seg_len_c[ic.tile];
         const int *rs_c = P.rowsrc_c + (size_t)ic.strip * nc;
-        for (int c = 0; c < nc; ++c) {
-            const long base = (long)rs_c[c] * P.pitch_uv + a0c;
-            unsigned char *dst = stage + (size_t)(nl + c) * P.slot_stride;
-            for (int b = lane; b < lenc; b += 32) {
-                const long g = base + b;
-                dst[b] = (g < P.plane_bytes_uv) ? __ldg(fr.uv + g) : (unsigned char)0;
-            }
-        }
+        for (int c = 0; c < nc; ++c)
+            copy_row_ldg(stage + (size_t)(nl + c) * P.slot_stride, fr.uv, (long)rs_c[c] * P.pitch_uv + a0c, lenc,
+                         P.plane_bytes_uv, lane);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);

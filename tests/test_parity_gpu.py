@@ -379,3 +379,35 @@ def test_error_codes_match_the_reference_contract(vp):
     with pytest.raises(vpp.VppError) as ei:
         vp.convert(y, uv, vpp.FrameParameters(pixel_format=1), width=0, height=0)
     assert str(ei.value) in ("-3", "1")
+
+
+def test_concurrent_consumers_share_one_processor(vp):
+    """Convert is called concurrently from several consumer threads in the reference (one CUDA
+    stream each, src/VideoProcessor.cpp:98-104); here: 4 threads, own torch streams, one context."""
+    import threading
+    kws = [SYNTH[0][4], dict(dst=(320, 240), resize_type=G.BICUBIC), dict(dst=(250, 150), resize_type=G.AREA),
+           dict(fourcc=G.Y800, normalization=True)]
+    frames = [_synthetic(1280, 720, seed=500 + i) for i in range(4)]
+    want = [_run_oracle(y, uv, kw) for (y, uv), kw in zip(frames, kws)]
+    errs = []
+
+    def worker(k):
+        try:
+            y, uv = frames[k]
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                ty, tuv = torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()
+                for _ in range(25):
+                    out = vp.convert(ty, tuv, _params(kws[k]))
+                s.synchronize()
+                if not _same(out.cpu().numpy().reshape(-1), want[k]):
+                    errs.append("thread %d: mismatch" % k)
+        except Exception as e:  # noqa: BLE001
+            errs.append("thread %d: %r" % (k, e))
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
