@@ -612,6 +612,24 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     const size_t off_cye = ar.add(cy_exact.data(), cy_exact.size() * sizeof(int));
     const size_t off_px = ar.add(patx.data(), patx.size() * sizeof(float));
     const size_t off_py = ar.add(paty.data(), paty.size() * sizeof(float));
+    // AREA: the divisor sum(px[b]*py[a]) does not depend on pixel data; evaluate it once per
+    // (vertical pattern row, horizontal pattern row) in the reference's order and rounding
+    // (Resize.cu:166-173: rows outer, columns inner, w = px*py, div += w), not 40 FADDs per sample
+    std::vector<float> area_div;
+    if (rs == RS_AREA) {
+        area_div.resize((size_t)PX * PY);
+        for (int r = 0; r < PY; ++r)
+            for (int c = 0; c < PX; ++c) {
+                float div = 0.f;
+                for (int a = 0; a < K; ++a)
+                    for (int b = 0; b < KX; ++b) {
+                        const float w = patx[(size_t)c * KX + b] * paty[(size_t)r * K + a];
+                        div = div + w;
+                    }
+                area_div[(size_t)r * PX + c] = div;
+            }
+    }
+    const size_t off_adiv = ar.add(area_div.data(), area_div.size() * sizeof(float));
 
     TSVPP_CUDA(cudaMalloc(&pl->dev_tables, ar.host.size() + 256));
     TSVPP_CUDA(cudaMemcpy(pl->dev_tables, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice));
@@ -643,6 +661,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     D.cy_exact = (const int *)(base + off_cye);
     D.px = (const float *)(base + off_px);
     D.py = (const float *)(base + off_py);
+    D.area_div = (const float *)(base + off_adiv);
 
     pl->rs = rs;
     pl->ok = ok;

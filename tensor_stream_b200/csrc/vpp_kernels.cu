@@ -345,6 +345,25 @@ struct ColOf<RS_BICUBIC> { using T = ColBicubic; };
 template <>
 struct ColOf<RS_AREA> { using T = ColArea; };
 
+// AREA window sum with the horizontal extent known at compile time: the KXT horizontal weights stay
+// in registers, the taps are immediate-offset shared loads.  Summation order and rounding are the
+// reference's (rows outer, columns inner; w = px*py; sum = fma(d, w, sum)).
+template <int KXT, int STRIDE>
+__device__ __noinline__ int area_sample(const unsigned char *s0, int slot_stride, int K, const float *__restrict__ px,
+                                        const float *__restrict__ py, float div) {
+    float pxr[KXT];
+#pragma unroll
+    for (int b = 0; b < KXT; ++b) pxr[b] = __ldg(px + b);
+    float sum = 0.0f;
+    for (int a = 0; a < K; ++a) {
+        const unsigned char *s = s0 + a * slot_stride;
+        const float wyv = __ldg(py + a);
+#pragma unroll
+        for (int b = 0; b < KXT; ++b) sum = __fmaf_rn(u2f(s[b * STRIDE]), __fmul_rn(pxr[b], wyv), sum);
+    }
+    return trunc_bits(__fdiv_rn(sum, div)) & 0xFF;
+}
+
 // `slots` points at slot 0 of this output row; `orow` is the output row index used to look up
 // the vertical weights (luma: i, chroma: ci -- the reference evaluates the *luma-grid* formula
 // at the chroma index, src/Resize.cu:303-310), `stride` is 1 for luma and 2 for chroma bytes,
@@ -372,18 +391,40 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
         return bicubic_dot_fast(cyf, P.cy + (size_t)orow * 4, __ldg(P.cy_exact + orow), b[0], b[1], b[2], b[3]);
     } else {
         // reference src/Resize.cu:160-178 (calculateAreaInterpolation): rows outer, columns
-        // inner; w = px*py; div += w; sum = fma(d, w, sum); (int)(sum/div)
+        // inner; w = px*py; sum = fma(d, w, sum); (int)(sum/div) -- div precomputed (same order)
         const float *px = P.px + (size_t)col.prow * P.KX;
-        const float *py = P.py + (size_t)(orow % P.PY) * P.K;
-        float sum = 0.0f, div = 0.0f;
-        for (int a = 0; a < P.K; ++a) {
-            const unsigned char *s = slots + a * P.slot_stride + col.o;
-            const float wyv = __ldg(py + a);
-            for (int b = 0; b < P.KX; ++b) {
-                const float w = __fmul_rn(__ldg(px + b), wyv);
-                div = __fadd_rn(div, w);
-                sum = __fmaf_rn(u2f(s[b * stride]), w, sum);
+        const int prow_y = orow % P.PY;
+        const float *py = P.py + (size_t)prow_y * P.K;
+        const float div = __ldg(P.area_div + (size_t)prow_y * P.PX + col.prow);
+        const unsigned char *s0 = slots + col.o;
+        if (stride == 1) {
+            switch (P.KX) {
+                case 2: return area_sample<2, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 3: return area_sample<3, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 4: return area_sample<4, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 5: return area_sample<5, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 6: return area_sample<6, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 7: return area_sample<7, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 8: return area_sample<8, 1>(s0, P.slot_stride, P.K, px, py, div);
+                default: break;
             }
+        } else {
+            switch (P.KX) {
+                case 2: return area_sample<2, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 3: return area_sample<3, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 4: return area_sample<4, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 5: return area_sample<5, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 6: return area_sample<6, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 7: return area_sample<7, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 8: return area_sample<8, 2>(s0, P.slot_stride, P.K, px, py, div);
+                default: break;
+            }
+        }
+        float sum = 0.0f;  // generic window width
+        for (int a = 0; a < P.K; ++a) {
+            const unsigned char *s = s0 + a * P.slot_stride;
+            const float wyv = __ldg(py + a);
+            for (int b = 0; b < P.KX; ++b) sum = __fmaf_rn(u2f(s[b * stride]), __fmul_rn(__ldg(px + b), wyv), sum);
         }
         return trunc_bits(__fdiv_rn(sum, div)) & 0xFF;
     }

@@ -83,6 +83,7 @@ struct PlanDev {
     const int *cy_exact;    // [nstrips*2*rp] 1 if the row's four weights are multiples of 2^-12
     const float *px;        // [PX][KX] AREA horizontal pattern
     const float *py;        // [PY][K]  AREA vertical pattern
+    const float *area_div;  // [PY][PX] sum of px[b]*py[a] in the kernel's order (rows outer, columns inner)
 };
 
 }  // namespace tsvpp
