@@ -608,6 +608,24 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     std::vector<int> cy_exact(cyw.size() / 4 + 1, 0);
     for (size_t i = 0; i < cyw.size(); ++i) cyf[i] = (float)cyw[i];
     for (size_t r = 0; r + 3 < cyw.size(); r += 4) cy_exact[r / 4] = weights_exact(&cyw[r]);
+    // bicubic: luma rows 2p and 2p+1 usually tap overlapping source rows; when row 2p+1's four
+    // source rows are row 2p's shifted by d (checked on the resolved row table, so the clamped
+    // borders simply report "no reuse"), its horizontal sums for taps k <= 3-d are row 2p's k+d
+    std::vector<int> row_shift((size_t)std::max(1, nrows_c), 4);
+    if (rs == RS_BICUBIC) {
+        for (int pr = 0; pr < nrows_c; ++pr) {
+            const int *r0 = &rowsrc_l[(size_t)(2 * pr) * K], *r1 = &rowsrc_l[(size_t)(2 * pr + 1) * K];
+            for (int d = 0; d <= 3; ++d) {
+                bool ok = true;
+                for (int k = 0; k + d <= 3; ++k) ok = ok && (r1[k] == r0[k + d]);
+                if (ok) {
+                    row_shift[pr] = d;
+                    break;
+                }
+            }
+        }
+    }
+    const size_t off_rshift = ar.add(row_shift.data(), row_shift.size() * sizeof(int));
     const size_t off_cyf = ar.add(cyf.data(), cyf.size() * sizeof(float));
     const size_t off_cye = ar.add(cy_exact.data(), cy_exact.size() * sizeof(int));
     const size_t off_px = ar.add(patx.data(), patx.size() * sizeof(float));
@@ -659,6 +677,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     D.cy = (const double *)(base + off_cy);
     D.cyf = (const float *)(base + off_cyf);
     D.cy_exact = (const int *)(base + off_cye);
+    D.row_shift = (const int *)(base + off_rshift);
     D.px = (const float *)(base + off_px);
     D.py = (const float *)(base + off_py);
     D.area_div = (const float *)(base + off_adiv);

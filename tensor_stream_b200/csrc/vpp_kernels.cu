@@ -430,6 +430,49 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
     }
 }
 
+// Bicubic, both luma rows of a block for one column.  Row 1 re-uses the horizontal sums of row 0
+// wherever the two rows tap the same source row (`shift`, warp-uniform, from the plan): the sum
+// depends on (source row, column) only, so this is the reference's arithmetic evaluated once
+// instead of twice.
+__device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, const unsigned char *sl0, const unsigned char *sl1,
+                                                  const ColBicubic &col, int i0, int shift, bool two_rows, int &y0,
+                                                  int &y1) {
+    const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
+    const float cf[4] = {col.cf[0], col.cf[1], col.cf[2], col.cf[3]};
+    const int exact_x = col.exact;
+    uint32_t b0[4], b1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned char *s = sl0 + k * P.slot_stride;
+        b0[k] = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
+    }
+    {
+        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(P.cyf) + i0);
+        const float cyf[4] = {c4.x, c4.y, c4.z, c4.w};
+        y0 = bicubic_dot_fast(cyf, P.cy + (size_t)i0 * 4, __ldg(P.cy_exact + i0), b0[0], b0[1], b0[2], b0[3]);
+    }
+    y1 = 0;
+    if (!two_rows) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // taps k <= 3-shift are row 0's k+shift; `shift` is uniform across the warp
+        bool reuse = false;
+        uint32_t v = 0;
+        if (shift == 0) { reuse = true; v = b0[k]; }
+        else if (shift == 1 && k <= 2) { reuse = true; v = b0[k + 1 > 3 ? 3 : k + 1]; }
+        else if (shift == 2 && k <= 1) { reuse = true; v = b0[k + 2 > 3 ? 3 : k + 2]; }
+        else if (shift == 3 && k == 0) { reuse = true; v = b0[3]; }
+        if (!reuse) {
+            const unsigned char *s = sl1 + k * P.slot_stride;
+            v = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
+        }
+        b1[k] = v;
+    }
+    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(P.cyf) + i0 + 1);
+    const float cyf[4] = {c4.x, c4.y, c4.z, c4.w};
+    y1 = bicubic_dot_fast(cyf, P.cy + (size_t)(i0 + 1) * 4, __ldg(P.cy_exact + i0 + 1), b1[0], b1[1], b1[2], b1[3]);
+}
+
 // ---------------------------------------------------------------------------------------
 // Colour conversion + layout for one block of 2 rows x BW columns (BW = 2 or 4) per thread
 // ---------------------------------------------------------------------------------------
@@ -681,6 +724,7 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
         const int ci = ic.strip * P.rp + ty;        // its chroma row
         const int j0 = colbase;                     // first output column
         float wy0 = 0.f, wy1 = 0.f, wyc = 0.f;
+        int row_shift = 4;
         if (active) {
             if (SMALL_COL && ic.tile != cur_tile) {
 #pragma unroll
@@ -695,6 +739,7 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
                 wy1 = __ldg(P.wy + i0 + 1);
                 wyc = __ldg(P.wy + ci);
             }
+            if (RS == RS_BICUBIC) row_shift = __ldg(P.row_shift + ci);
         }
 
         mbar_wait(full + s, phase);
@@ -714,8 +759,12 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
             for (int b = 0; b < BW; ++b) {
                 if (b < nx) {
                     const ColT &L = SMALL_COL ? lreg[b] : col_l[colbase + b];
-                    Yv[0][b] = resample<RS>(P, sl0, L, i0, 1, wy0);
-                    if (ny > 1) Yv[1][b] = resample<RS>(P, sl1, L, i0 + 1, 1, wy1);
+                    if constexpr (RS == RS_BICUBIC) {
+                        bicubic_luma_pair(P, sl0, sl1, L, i0, row_shift, ny > 1, Yv[0][b], Yv[1][b]);
+                    } else {
+                        Yv[0][b] = resample<RS>(P, sl0, L, i0, 1, wy0);
+                        if (ny > 1) Yv[1][b] = resample<RS>(P, sl1, L, i0 + 1, 1, wy1);
+                    }
                 }
             }
             if (NEED_UV && ci < P.ch2) {

@@ -81,6 +81,8 @@ struct PlanDev {
     const double *cy;       // [nstrips*2*rp][4] bicubic vertical weights per output row index
     const float *cyf;       // same, rounded to f32
     const int *cy_exact;    // [nstrips*2*rp] 1 if the row's four weights are multiples of 2^-12
+    const int *row_shift;   // [nstrips*rp] bicubic: source-row window of luma row 2p+1 = that of row 2p shifted by
+                            // this many rows (0..3), 4 = no reuse; lets row 2p+1 reuse row 2p's horizontal sums
     const float *px;        // [PX][KX] AREA horizontal pattern
     const float *py;        // [PY][K]  AREA vertical pattern
     const float *area_div;  // [PY][PX] sum of px[b]*py[a] in the kernel's order (rows outer, columns inner)
