@@ -458,7 +458,10 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
                 const int by_smem = (int)((size_t)(228 * 1024) / (smem + 1024));
                 const int ctas = std::max(1, std::min(std::min(by_smem, reg_ctas), 2048 / threads));
                 // one stage can only be refilled while another is consumed: a single stage serialises
-                const long score = (long)ctas * consumers * (ns >= 2 ? 8 : 1) * 64 + (cand / 32) * 4 + std::min(ns, 3);
+                // resident consumer threads, discounted by the share of the CTA that is the producer warp
+                // (small CTAs spend a third of their warps on issuing ever smaller copies)
+                const long eff = (long)ctas * consumers * consumers / (consumers + 32);
+                const long score = eff * (ns >= 2 ? 8 : 1) * 64 + (cand / 32) * 4 + std::min(ns, 3);
                 if (score > best_score) {
                     best_score = score;
                     found = true;
