@@ -280,6 +280,11 @@ struct TsvppContext {
 struct TsvppBatch {
     TsvppContext *ctx = nullptr;
     Plan *plan = nullptr;
+    // UYVY / YUV444 batches replay the two-kernel path from a host copy of the descriptors
+    bool packed_yuv = false;
+    TsvppParams params{};
+    std::vector<TsvppFrame> frames;
+    std::vector<void *> outs;
     FrameDev *frames_dev = nullptr;
     int n = 0;
     int vec_ok = 0;
@@ -950,6 +955,17 @@ int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const
     if (!ctx || !frames || !p || !out || !batch || n <= 0) return TSVPP_ERROR;
     int rc = check_uniform(frames, n);
     if (rc) return rc;
+    if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444) {
+        std::unique_ptr<TsvppBatch> b(new TsvppBatch());
+        b->ctx = ctx;
+        b->packed_yuv = true;
+        b->params = *p;
+        b->n = n;
+        b->frames.assign(frames, frames + n);
+        b->outs.assign(out, out + n);
+        *batch = b.release();
+        return TSVPP_OK;
+    }
     const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
     Plan *pl = nullptr;
     rc = get_plan(ctx, frames[0], *p, bulk, &pl);
@@ -974,6 +990,8 @@ int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const
 
 int tsvpp_batch_run(TsvppBatch *b, void *stream) {
     if (!b) return TSVPP_ERROR;
+    if (b->packed_yuv)
+        return tsvpp_convert_batch(b->ctx, b->frames.data(), b->n, &b->params, b->outs.data(), stream);
     const Plan *pl = b->plan;
     (void)cudaGetLastError();
     int rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, b->frames_dev, b->n, b->vec_ok, b->grid, pl->smem,

@@ -411,3 +411,25 @@ def test_concurrent_consumers_share_one_processor(vp):
     for t in ths:
         t.join()
     assert not errs, errs
+
+
+def test_prebuilt_batch_handles_every_fourcc(vp):
+    """tsvpp_batch_create/run (descriptor ring uploaded once) for a fused format and for the
+    two-kernel UYVY / YUV444 path."""
+    frames = [_synthetic(1280, 720, seed=600 + i) for i in range(3)]
+    dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
+    for kw in (dict(dst=(320, 240), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True),
+               dict(dst=(320, 240), resize_type=G.AREA, fourcc=G.UYVY), dict(fourcc=G.YUV444, normalization=True)):
+        from tensor_stream_b200 import vpp
+        fp = _params(kw)
+        shape, es = vpp.output_shape(1280, 720, fp)
+        outs = [torch.zeros(shape, dtype=torch.float32 if es == 4 else torch.uint8, device="cuda") for _ in dev]
+        b = vp.make_batch(dev, fp, outs)
+        b.run()
+        b.run()
+        torch.cuda.synchronize()
+        for (y, uv), o in zip(frames, outs):
+            got = _mask_undefined(o.cpu().numpy().reshape(-1), kw, 1280, 720)
+            want = _mask_undefined(_run_oracle(y, uv, kw), kw, 1280, 720)
+            assert _same(got, want), _diff_report(got, want)
+        b.destroy()
