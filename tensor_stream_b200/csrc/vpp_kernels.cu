@@ -171,16 +171,24 @@ __device__ __forceinline__ ChromaTerms chroma_terms(int U, int V) {
     t.g = __fadd_rn(g, 0.5f);
     return t;
 }
-// one pixel -> the three channels as "magic" bit patterns clamped to [2^23+0, 2^23+255]
+// (int)v clamped to [0,255] in ONE instruction: a float->u8 conversion truncates toward zero and
+// saturates to the destination range (PTX cvt semantics), i.e. exactly min(max((int)v,0),255) of
+// reference src/ColorConversion.cu:26-38.  It runs on the XU pipe, which this kernel otherwise
+// leaves idle, and replaces FADD.RZ + 2 IMNMX + LOP on the busy FMA/ALU pipes.
+__device__ __forceinline__ uint32_t f2u8_sat(float v) {
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+// one pixel -> the three channels, each already clamped to 0..255
 __device__ __forceinline__ void yuv_px_bits(int Y, const ChromaTerms &t, int &R, int &G, int &B) {
     // max(0, Y-16) on integers first: identical to max(0.f, (float)Y - 16.f)
     const float yp = u2f((uint32_t)max(Y - 16, 0));
-    const int lo = (int)kMagicBits, hi = (int)kMagicBits + 255;
-    R = min(max(trunc_bits(__fmaf_rn(yp, 1.163999557f, t.r)), lo), hi);
-    G = min(max(trunc_bits(__fmaf_rn(yp, 1.163999557f, t.g)), lo), hi);
-    B = min(max(trunc_bits(__fmaf_rn(yp, 1.163999557f, t.b)), lo), hi);
+    R = (int)f2u8_sat(__fmaf_rn(yp, 1.163999557f, t.r));
+    G = (int)f2u8_sat(__fmaf_rn(yp, 1.163999557f, t.g));
+    B = (int)f2u8_sat(__fmaf_rn(yp, 1.163999557f, t.b));
 }
-__device__ __forceinline__ uint32_t bits_u8(int bits) { return (uint32_t)bits & 0xFFu; }
+__device__ __forceinline__ uint32_t bits_u8(int c) { return (uint32_t)c; }
 
 // c / 255.0f with IEEE rounding for c in 0..255 given as magic bits: reciprocal multiply plus one
 // residual correction; verified exhaustively against the division (tests/test_host_logic.py).
@@ -190,7 +198,7 @@ __device__ __forceinline__ float div255_x(float x) {
     const float e = __fmaf_rn(-q, 255.0f, x);
     return __fmaf_rn(e, r, q);
 }
-__device__ __forceinline__ float div255_bits(int bits) { return div255_x(__fsub_rn(__int_as_float(bits), kMagic)); }
+__device__ __forceinline__ float div255_bits(int c) { return div255_x(u2f((uint32_t)c)); }
 __device__ __forceinline__ float div255_u8(uint32_t c) { return div255_x(u2f(c)); }
 
 // reference src/ColorConversion.cu:235-278 (RGBMergedToHSVMerged<float>)
@@ -568,7 +576,7 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
             }
         }
     } else {
-        // RGB family: channel values as magic bit patterns, [row][col][channel]
+        // RGB family: channel values 0..255, [row][col][channel]
         int C[2][BW][3];
 #pragma unroll
         for (int p = 0; p < BW / 2; ++p) {
