@@ -102,6 +102,16 @@ __device__ __forceinline__ float u2f(uint32_t b) {
 // v yields bits < kMagicBits (only ever used before a clamp at 0)
 __device__ __forceinline__ int trunc_bits(float v) { return __float_as_int(__fadd_rz(v, kMagic)); }
 
+// (int)v clamped to [0,255] in ONE instruction (SASS F2IP.U8.F32.TRUNC): a float->u8 conversion
+// truncates toward zero and saturates to the destination range (PTX cvt semantics), i.e. exactly
+// min(max((int)v,0),255) of reference src/ColorConversion.cu:26-38 -- and exactly (unsigned char)(int)v
+// for the resamplers, whose results lie in [0,256).  Replaces FADD.RZ + 2 IMNMX + LOP.
+__device__ __forceinline__ uint32_t f2u8_sat(float v) {
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // Arithmetic shared with the oracle (each cites the reference lines it reproduces)
 // ---------------------------------------------------------------------------------------
@@ -115,7 +125,7 @@ __device__ __forceinline__ int bilinear_px(uint32_t a, uint32_t b, uint32_t c, u
     float v = __fmaf_rn(__fmul_rn(A, omx), omy, __fmul_rn(__fmul_rn(B, wx), omy));
     v = __fmaf_rn(omx, __fmul_rn(C, wy), v);
     v = __fmaf_rn(D, __fmul_rn(wx, wy), v);
-    return trunc_bits(v) & 0xFF;
+    return (int)f2u8_sat(v);
 }
 
 // reference src/Resize.cu:45-59: one 4-tap row of the bicubic, DFMA chain as compiled
@@ -170,15 +180,6 @@ __device__ __forceinline__ ChromaTerms chroma_terms(int U, int V) {
     g = __fmaf_rn(fv, -0.812999725f, g);
     t.g = __fadd_rn(g, 0.5f);
     return t;
-}
-// (int)v clamped to [0,255] in ONE instruction: a float->u8 conversion truncates toward zero and
-// saturates to the destination range (PTX cvt semantics), i.e. exactly min(max((int)v,0),255) of
-// reference src/ColorConversion.cu:26-38.  It runs on the XU pipe, which this kernel otherwise
-// leaves idle, and replaces FADD.RZ + 2 IMNMX + LOP on the busy FMA/ALU pipes.
-__device__ __forceinline__ uint32_t f2u8_sat(float v) {
-    uint32_t r;
-    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
 }
 // one pixel -> the three channels, each already clamped to 0..255
 __device__ __forceinline__ void yuv_px_bits(int Y, const ChromaTerms &t, int &R, int &G, int &B) {
@@ -369,7 +370,7 @@ __device__ __noinline__ int area_sample(const unsigned char *s0, int slot_stride
 #pragma unroll
         for (int b = 0; b < KXT; ++b) sum = __fmaf_rn(u2f(s[b * STRIDE]), __fmul_rn(pxr[b], wyv), sum);
     }
-    return trunc_bits(__fdiv_rn(sum, div)) & 0xFF;
+    return (int)f2u8_sat(__fdiv_rn(sum, div));
 }
 
 // `slots` points at slot 0 of this output row; `orow` is the output row index used to look up
@@ -434,7 +435,7 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
             const float wyv = __ldg(py + a);
             for (int b = 0; b < P.KX; ++b) sum = __fmaf_rn(u2f(s[b * stride]), __fmul_rn(__ldg(px + b), wyv), sum);
         }
-        return trunc_bits(__fdiv_rn(sum, div)) & 0xFF;
+        return (int)f2u8_sat(__fdiv_rn(sum, div));
     }
 }
 
