@@ -190,3 +190,19 @@ def test_product_code_never_imports_the_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle|liboracle|vpp_oracle\.h", txt, re.M):
                         bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_c_abi_header_is_plain_c(lib, tmp_path):
+    """include/tsvpp.h must be consumable from C (cgo / JNI / FFI generators): C99, no C++ types."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "tsvpp.h"\n'
+                   "int probe(void) { TsvppParams p = {0,0,0,0, 256,256, TSVPP_BILINEAR, TSVPP_BGR24, TSVPP_PLANAR, 1};\n"
+                   "  int w, h, es; size_t n; return tsvpp_output_info(1920, 1080, &p, &w, &h, &n, &es) + (int)n + w + h + es; }\n")
+    so = tmp_path / "libuse.so"
+    libdir = os.path.join(ROOT, "tensor_stream_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-shared", "-fPIC", "-I",
+                           os.path.join(ROOT, "include"), str(src), "-o", str(so), "-L", libdir, "-l:libtsvpp.so",
+                           "-Wl,-rpath," + libdir])
+    probe = C.CDLL(str(so)).probe
+    probe.restype = C.c_int
+    assert probe() == 0 + 3 * 256 * 256 + 256 + 256 + 4
