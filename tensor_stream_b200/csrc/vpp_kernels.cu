@@ -154,14 +154,14 @@ __device__ __forceinline__ int bicubic_dot_fast(const float *cf, const double *c
     s = __fmaf_rn(cf[2], u2f(d2), s);
     s = __fmaf_rn(cf[3], u2f(d3), s);
     const float t = __fadd_rn(s, 0.5f);
-    const int bits = trunc_bits(t);  // 2^23 + floor(t) for t >= 0; below 2^23 for t < 0 (clamps to 0)
+    const uint32_t r = f2u8_sat(t);  // floor(t) for 0 <= t < 256, saturated outside: clamp(round-half-up(s))
     if (!exact) {
-        const float frac = __fsub_rn(t, __fsub_rn(__int_as_float(bits), kMagic));
-        const float eps = 0.001953125f;  // 2^-9
+        const float frac = __fsub_rn(t, u2f(r));  // in [0,1) wherever the rounding can matter
+        const float eps = 0.001953125f;           // 2^-9
         if (t >= 0.0f && (frac < eps || frac > 1.0f - eps))
             return bicubic_dot(cd[0], cd[1], cd[2], cd[3], (int)d0, (int)d1, (int)d2, (int)d3);
     }
-    return (int)(min(max(bits, (int)kMagicBits), (int)kMagicBits + 255) & 0xFF);
+    return (int)r;
 }
 
 // reference src/ColorConversion.cu:6-39 (NV12toRGB24Kernel); chroma terms are shared by the
