@@ -105,6 +105,26 @@ int main(int argc, char **argv) {
         if (last == VREADER_OK) cudaFree(o2.opaque);
     }
     std::printf("sixth_consumer %d\n", last);
+    // optional: per-frame Convert rate through the drop-in API (argv[15] = iterations)
+    if (argc > 15) {
+        const int iters = std::atoi(argv[15]);
+        cudaDeviceSynchronize();
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int k = 0; k < iters; ++k) {
+            AVFrame o2 = {};
+            FrameParameters fa = {resize, color, crop};
+            if (VPP.Convert(&in, &o2, fa, "visualize") != VREADER_OK) return 7;
+            cudaFree(o2.opaque);
+        }
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        std::printf("convert_per_frame_fps %.0f\n", iters / (ms * 1e-3));
+    }
     VPP.Close();
     cudaFree(dY);
     cudaFree(dUV);
