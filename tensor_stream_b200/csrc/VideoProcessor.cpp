@@ -10,6 +10,7 @@
 // intermediates in HBM and the per-frame AREA pattern upload.
 #include "VideoProcessor.h"
 
+#include <cstdint>
 #include <cstdlib>
 
 #include "tsvpp.h"
@@ -70,6 +71,14 @@ int VideoProcessor::Init(std::shared_ptr<Logger> lg, uint8_t maxConsumers, bool 
     if (e != cudaSuccess) return (int)e;
     int rc = tsvpp_create(device, &ctx);
     if (rc) return rc;
+    // Results come from the device's default memory pool (cudaMallocAsync) and callers release them
+    // with cudaFree, which synchronises; keep the freed blocks in the pool instead of handing them
+    // back to the OS at every synchronisation, or each Convert would pay a fresh OS allocation.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     for (int i = 0; i < maxConsumers; ++i) {
         cudaStream_t s;
         // blocking streams like the reference (:86): implicitly ordered against the legacy default stream
