@@ -453,7 +453,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             const size_t stage = (size_t)nslots * stride;
             const size_t fixed = 2 * 8 * kMaxStages + 128;
             const int consumers = (cand / bw) * cand_rp;
-            const int threads = 32 + round_up(consumers, 32);
+            const int threads = 32 * (bulk ? 1 : kLdgProducerWarps) + round_up(consumers, 32);
             const int reg_ctas = std::max(1, 65536 / (threads * regs_assumed));
             for (int ns = (want_ns > 0 ? want_ns : 4); ns >= 1; --ns) {
                 if (want_ns > 0 && ns != want_ns) continue;
@@ -664,6 +664,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     PlanDev &D = pl->dev;
     D.dw = dw; D.dh = dh; D.cw2 = cw2; D.ch2 = ch2;
     D.tw = tw; D.ntiles = ntiles; D.nstrips = nstrips; D.rp = rp; D.bw = bw;
+    D.nprod = bulk ? 1 : kLdgProducerWarps;
     D.K = K; D.KX = KX;
     D.slot_stride = slot_stride;
     D.stage_bytes = (need_uv ? 3 : 2) * rp * K * slot_stride;

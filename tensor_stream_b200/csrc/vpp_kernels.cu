@@ -321,23 +321,24 @@ __device__ __forceinline__ void copy_row_ldg(unsigned char *dst, const unsigned 
 
 template <bool NEED_UV>
 __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev *__restrict__ frames,
-                                               const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane) {
+                                               const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane,
+                                               int pwarp, int npwarps) {
     const FrameDev fr = frames[ic.frame];
     const int nl = 2 * P.rp * P.K;
     const int nc = NEED_UV ? P.rp * P.K : 0;
     const int a0l = P.seg_a0_l[ic.tile], lenl = P.seg_len_l[ic.tile];
     const int *rs_l = P.rowsrc_l + (size_t)ic.strip * nl;
-    for (int c = 0; c < nl; ++c)
+    for (int c = pwarp; c < nl; c += npwarps)  // rows are dealt round-robin to the producer warps
         copy_row_ldg(stage + (size_t)c * P.slot_stride, fr.y, (long)rs_l[c] * P.pitch_y + a0l, lenl, P.plane_bytes_y, lane);
     if (NEED_UV) {
         const int a0c = P.seg_a0_c[ic.tile], lenc = P.seg_len_c[ic.tile];
         const int *rs_c = P.rowsrc_c + (size_t)ic.strip * nc;
-        for (int c = 0; c < nc; ++c)
+        for (int c = pwarp; c < nc; c += npwarps)
             copy_row_ldg(stage + (size_t)(nl + c) * P.slot_stride, fr.uv, (long)rs_c[c] * P.pitch_uv + a0c, lenc,
                          P.plane_bytes_uv, lane);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    if (lane == 0) mbar_arrive(bar);  // the "full" barrier counts one arrival per producer warp
 }
 
 // ---------------------------------------------------------------------------------------
@@ -659,7 +660,8 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
 // every consumer thread owns a block of 2 rows x BW columns of the output.
 // ---------------------------------------------------------------------------------------
 template <int RS, int OK, bool BULK, int BW>
-__global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((RS == RS_BICUBIC || RS == RS_AREA) ? 3 : 4))
+__global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? 0 : 32 * (kLdgProducerWarps - 1)),
+                                  BULK ? (BW == 4 ? 5 : ((RS == RS_BICUBIC || RS == RS_AREA) ? 3 : 4)) : 2)
     vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     using ColT = typename ColOf<RS>::T;
@@ -671,7 +673,8 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
     unsigned char *stages = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * P.stage_bytes);
     uint64_t *empty = full + kMaxStages;
-    const int ncons_warps = ((int)blockDim.x >> 5) - 1;
+    constexpr int NPROD = BULK ? 1 : kLdgProducerWarps;  // producer warps
+    const int ncons_warps = ((int)blockDim.x >> 5) - NPROD;
 
     const int total = nframes * P.nstrips * P.ntiles;
     const int first = blockIdx.x;
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(full + s, 1);
+            mbar_init(full + s, (uint32_t)NPROD);
             mbar_init(empty + s, (uint32_t)ncons_warps);
         }
         fence_barrier_init();
@@ -687,8 +690,8 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ================= producer =================
+    if (warp < NPROD) {
+        // ================= producer(s) =================
         const uint64_t policy = l2_policy_evict_first();
         ItemIter ic;
         ic.init(P, first, (int)gridDim.x);
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
             if (BULK)
                 issue_stage_bulk<NEED_UV>(P, frames, ic, stage, full + s, lane, policy);
             else
-                fill_stage_ldg<NEED_UV>(P, frames, ic, stage, full + s, lane);
+                fill_stage_ldg<NEED_UV>(P, frames, ic, stage, full + s, lane, warp, NPROD);
             if (++s == NS) {
                 s = 0;
                 phase ^= 1u;
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(BW == 4 ? 160 : kMaxThreads, BW == 4 ? 5 : ((R
     }
 
     // ================= consumers =================
-    const int ctid = tid - 32;
+    const int ctid = tid - 32 * NPROD;
     const int blocks_x = P.tw / BW;
     const int tx = ctid % blocks_x;  // column block inside the tile
     const int ty = ctid / blocks_x;  // row pair inside the strip
@@ -884,7 +887,7 @@ bool fused_supports_bw4(int rs) { return rs == RS_NEAREST || rs == RS_BILINEAR; 
 
 int fused_block_threads(const PlanDev &P) {
     const int cons = (P.tw / P.bw) * P.rp;
-    return 32 + (cons + 31) / 32 * 32;
+    return 32 * P.nprod + (cons + 31) / 32 * 32;
 }
 
 size_t fused_smem_bytes(const PlanDev &P) {
