@@ -11,16 +11,20 @@
 //                   source-row segment into a ring of shared-memory stages; completion is
 //                   tracked by "full" mbarriers, reuse by "empty" mbarriers.  Only the source
 //                   rows / bytes the taps touch are ever fetched from HBM.
-//   consumer warps: each thread owns one 2x2 block of output pixels: 4 luma samples and the one
-//                   (U,V) pair they share are resampled from the staged rows with the
+//                   Frames whose base / pitch are not 16-byte aligned are filled by four producer
+//                   warps with guarded aligned loads + funnel shifts instead (same consumers).
+//   consumer warps: each thread owns a block of 2 rows x BW columns (BW = 2, or 4 for wide outputs
+//                   of the light resamplers): the luma samples and the (U,V) pairs they share
+//                   are resampled from the staged rows with the
 //                   reference's exact arithmetic (explicit __f*_rn intrinsics so the FMA
 //                   positions equal the reference's nvcc -fmad=true contraction), rounded
 //                   through uint8 exactly where the reference stores its NV12 intermediate,
 //                   then converted (BT.601), normalised and stored with vector stores.
 //                   No block-wide barrier anywhere in the steady state.
-// uint8 -> float uses cvt.rn.f32.u32 on 32-bit registers (I2FP, full rate) and float -> uint8 the
-// 2^23 magic-number form (FADD.RZ + LOP) instead of the byte-typed I2F/F2I forms (quarter-rate XU
-// pipe): ncu showed XU as the busiest pipe of the first version.
+// uint8 -> float uses cvt.rn.f32.u32 on 32-bit registers (SASS I2FP) and float -> uint8 one
+// saturating cvt.rzi.u8.f32 (SASS F2IP: truncation and the [0,255] clamp in one instruction)
+// instead of the byte-typed I2F/F2I forms the compiler picks for (float)uchar / (int)float
+// (quarter-rate XU pipe: ncu showed XU as the busiest pipe of the first version).
 // Bit-exactness contract: see oracle/vpp_oracle.c (same formulas, same citations).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -98,9 +102,6 @@ __device__ __forceinline__ float u2f(uint32_t b) {
     return f;
 #endif
 }
-// bits of (2^23 + trunc(v)) for |v| < 2^22: (int)v == bits - kMagicBits when v >= 0; any negative
-// v yields bits < kMagicBits (only ever used before a clamp at 0)
-__device__ __forceinline__ int trunc_bits(float v) { return __float_as_int(__fadd_rz(v, kMagic)); }
 
 // (int)v clamped to [0,255] in ONE instruction (SASS F2IP.U8.F32.TRUNC): a float->u8 conversion
 // truncates toward zero and saturates to the destination range (PTX cvt semantics), i.e. exactly
