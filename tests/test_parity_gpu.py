@@ -205,6 +205,12 @@ SYNTH += [
     ("yuv444_noresize_f32", 640, 360, 640, dict(fourcc=G.YUV444, normalization=True)),
     ("yuv444_crop_bicubic", 1280, 720, 1280, dict(crop=(64, 32, 704, 512), dst=(320, 200), resize_type=G.BICUBIC, fourcc=G.YUV444)),
     ("uyvy_area_f32", 1280, 720, 1280, dict(dst=(426, 240), resize_type=G.AREA, fourcc=G.UYVY, normalization=True)),
+    # maximum sizes: 8K sources / outputs (NEAREST, AREA and BICUBIC index with integers in the reference;
+    # its BILINEAR start index is float math that is only exact below 2^24 pixels per plane)
+    ("src_8k_nearest", 7680, 4320, 7680, dict(dst=(512, 512), resize_type=G.NEAREST, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
+    ("src_8k_area_generic_window", 7680, 4320, 7680, dict(dst=(480, 270), resize_type=G.AREA)),
+    ("src_8k_bicubic_crop", 7680, 4320, 7680, dict(crop=(1920, 1080, 5760, 3240), dst=(640, 360), resize_type=G.BICUBIC)),
+    ("dst_8k_nearest", 1920, 1080, 1920, dict(dst=(7680, 4320), resize_type=G.NEAREST)),
 ]
 
 
