@@ -256,6 +256,7 @@ struct Plan {
 
 struct TsvppContext {
     int device = 0;
+    bool frames_in_host_memory = false;  // set around launches of the zero-copy host path
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;
     std::mutex mu;
@@ -412,6 +413,8 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     int bw = (fused_supports_bw4(rs) && dw % 4 == 0 && dw >= 512 && (rs == RS_NEAREST || (xr >= 1.0f && yr >= 1.0f))) ? 4 : 2;
     if (env_int("TSVPP_BW", 0) == 2) bw = 2;
     if (env_int("TSVPP_BW", 0) == 4 && fused_supports_bw4(rs) && dw % 4 == 0) bw = 4;
+    int nprod_bulk = 1;  // bulk-copy producer warps (2 only with 4-column blocks: __launch_bounds__)
+    if (bw == 4 && env_int("TSVPP_NPROD", 1) == 2) nprod_bulk = 2;
     const int regs_assumed = bw == 4 ? 80 : ((rs == RS_NEAREST || rs == RS_BILINEAR) ? 56 : 72);  // caps implied by __launch_bounds__
     long best_score = -1;
     for (int cand_rp = 2; cand_rp >= 1; --cand_rp) {
@@ -453,7 +456,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             const size_t stage = (size_t)nslots * stride;
             const size_t fixed = 2 * 8 * kMaxStages + 128;
             const int consumers = (cand / bw) * cand_rp;
-            const int threads = 32 * (bulk ? 1 : kLdgProducerWarps) + round_up(consumers, 32);
+            const int threads = 32 * (bulk ? nprod_bulk : kLdgProducerWarps) + round_up(consumers, 32);
             const int reg_ctas = std::max(1, 65536 / (threads * regs_assumed));
             for (int ns = (want_ns > 0 ? want_ns : 4); ns >= 1; --ns) {
                 if (want_ns > 0 && ns != want_ns) continue;
@@ -543,12 +546,21 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     DeviceArena ar;
     size_t off_col_l = 0, off_col_c = 0;
     auto rel = [&](int abs_pos, int a0) { return std::max(0, abs_pos - a0); };
+    int ident = 0;
     if (rs == RS_NEAREST) {
         std::vector<ColNearest> cl(ncol, ColNearest{0}), cc(ncol, ColNearest{0});
         for (int j = 0; j < dw; ++j) {
             const int t = j / tw;
             cl[j].o = rel(tap_l[(size_t)j * 4], a0l[t]);
             if (need_uv && lo_c[j] >= 0) cc[j].o = rel(tap_c[(size_t)j * 4], a0c[t]);
+        }
+        ident = 1;
+        for (int j0 = 0; j0 + bw <= dw && ident; j0 += bw) {
+            for (int b = 0; b < bw; ++b) {
+                if (cl[j0 + b].o != cl[j0].o + b) ident = 0;
+                if (need_uv && (lo_c[j0 + b] < 0 || cc[j0 + b].o != cc[j0].o + b)) ident = 0;
+            }
+            if (cl[j0].o % bw || (need_uv && cc[j0].o % bw)) ident = 0;
         }
         off_col_l = ar.add(cl.data(), cl.size() * sizeof(ColNearest));
         off_col_c = ar.add(cc.data(), cc.size() * sizeof(ColNearest));
@@ -664,7 +676,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     PlanDev &D = pl->dev;
     D.dw = dw; D.dh = dh; D.cw2 = cw2; D.ch2 = ch2;
     D.tw = tw; D.ntiles = ntiles; D.nstrips = nstrips; D.rp = rp; D.bw = bw;
-    D.nprod = bulk ? 1 : kLdgProducerWarps;
+    D.nprod = bulk ? nprod_bulk : kLdgProducerWarps;
     D.K = K; D.KX = KX;
     D.slot_stride = slot_stride;
     D.stage_bytes = (need_uv ? 3 : 2) * rp * K * slot_stride;
@@ -673,6 +685,28 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     D.plane_bytes_y = plane_y; D.plane_bytes_uv = plane_uv;
     D.swap_rb = (p.fourcc == TSVPP_BGR24) ? 1 : 0;  // ColorConversion.cu:305
     D.need_uv = need_uv ? 1 : 0;
+    D.ident = ident;
+    // direct path: no resize (rows and columns affine with unit step, nothing clamped), 4-column
+    // blocks, 32-bit aligned loads
+    {
+        bool direct = rs == RS_NEAREST && bulk && dw % 4 == 0 && dh % 2 == 0 && dw >= 4 && dh >= 2 &&
+                      !env_int("TSVPP_NO_DIRECT", 0);
+        for (int j = 0; j < dw && direct; ++j) {
+            if (tap_l[(size_t)j * 4] != tap_l[0] + j) direct = false;
+            if (need_uv && (lo_c[j] < 0 || tap_c[(size_t)j * 4] != tap_c[0] + j)) direct = false;
+        }
+        for (int i = 0; i < dh && direct; ++i)
+            if (rowsrc_l[(size_t)i * K] != rowsrc_l[0] + i) direct = false;
+        if (need_uv)
+            for (int ci = 0; ci < dh / 2 && direct; ++ci)
+                if (rowsrc_c[(size_t)ci * K] != rowsrc_c[0] + ci) direct = false;
+        if (direct && ((tap_l[0] & 3) || (need_uv && (tap_c[0] & 3)))) direct = false;
+        D.direct = direct ? 1 : 0;
+        D.d_row_l0 = direct ? rowsrc_l[0] : 0;
+        D.d_row_c0 = (direct && need_uv) ? rowsrc_c[0] : 0;
+        D.d_x_l0 = direct ? tap_l[0] : 0;
+        D.d_x_c0 = (direct && need_uv) ? tap_c[0] : 0;
+    }
     D.PX = PX; D.PY = PY;
     D.seg_a0_l = (const int *)(base + off_a0l);
     D.seg_len_l = (const int *)(base + off_lenl);
@@ -715,9 +749,9 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     static const char *rs_names[] = {"nearest", "bilinear", "bicubic", "area"};
     std::snprintf(buf, sizeof(buf),
                   "resample=%s out_kind=%d fill=%s bw=%d tw=%d rp=%d K=%d KX=%d ntiles=%d nstrips=%d slot_stride=%d "
-                  "stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d crop=%d resize=%d fetch_bytes_per_frame=%ld",
+                  "stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d crop=%d resize=%d fetch_bytes_per_frame=%ld direct=%d",
                   rs_names[rs], ok, bulk ? "bulk" : "ldg", bw, tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
-                  nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize, fetch);
+                  nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize, fetch, D.direct);
     pl->desc = buf;
     out = std::move(pl);
     return TSVPP_OK;
@@ -768,9 +802,20 @@ int vec_ok_for(const Plan *pl, void *const *out, int n) {
     return 1;
 }
 
+// device-resident frames of a no-resize plan skip the staging ring (vpp_direct_kernel)
+int launch_plan(const Plan *pl, const FrameDev *frames_dev, int n, int vec_ok, int grid, cudaStream_t stream,
+                bool allow_direct) {
+    if (pl->dev.direct && allow_direct) return launch_direct(pl->ok, pl->dev, frames_dev, n, vec_ok, stream);
+    return launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, frames_dev, n, vec_ok, grid, pl->smem, stream);
+}
+
 int grid_for(const TsvppContext *ctx, const Plan *pl, int n) {
     const long items = (long)n * pl->dev.nstrips * pl->dev.ntiles;
-    const long cap = (long)ctx->sm_count * pl->ctas_per_sm;
+    long cap = (long)ctx->sm_count * pl->ctas_per_sm;
+    // a CTA's items advance by gridDim.x and the tile is the fastest-varying item coordinate: with
+    // the grid a multiple of ntiles every CTA keeps ONE column tile for its whole life, so its
+    // column tap tables are loaded once instead of once per item
+    if (cap > pl->dev.ntiles) cap -= cap % pl->dev.ntiles;
     return (int)std::max(1L, std::min(items, cap));
 }
 
@@ -943,8 +988,8 @@ int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, cons
     rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
     if (rc) return rc;
     (void)cudaGetLastError();  // drop stale non-sticky errors of unrelated earlier calls
-    rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n),
-                      grid_for(ctx, pl, n), pl->smem, stream);
+    rc = launch_plan(pl, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n), grid_for(ctx, pl, n), stream,
+                     !ctx->frames_in_host_memory);
     TSVPP_CUDA(cudaEventRecord(ctx->ring_ev[slot], stream));
     ctx->launches.fetch_add(1);
     if (rc) return note_error(rc, "launch_fused", __LINE__);
@@ -995,8 +1040,7 @@ int tsvpp_batch_run(TsvppBatch *b, void *stream) {
         return tsvpp_convert_batch(b->ctx, b->frames.data(), b->n, &b->params, b->outs.data(), stream);
     const Plan *pl = b->plan;
     (void)cudaGetLastError();
-    int rc = launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, b->frames_dev, b->n, b->vec_ok, b->grid, pl->smem,
-                          (cudaStream_t)stream);
+    int rc = launch_plan(pl, b->frames_dev, b->n, b->vec_ok, b->grid, (cudaStream_t)stream, true);
     b->ctx->launches.fetch_add(1);
     if (rc) return note_error(rc, "launch_fused", __LINE__);
     return rc;
@@ -1090,7 +1134,9 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
             f[i].y = zy[i];
             f[i].uv = zuv[i];
         }
+        ctx->frames_in_host_memory = true;  // in-place reads over PCIe: keep the bulk-copy row fetches
         rc = tsvpp_convert_batch(ctx, f.data(), n, p, zout.data(), ctx->hstream[0]);
+        ctx->frames_in_host_memory = false;
         if (rc) return rc;
         TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
         return TSVPP_OK;
@@ -1116,7 +1162,9 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
             }
             douts[k] = zc_out ? zout[base + k] : (void *)(ctx->stage_out[which] + out_frame * k);
         }
+        ctx->frames_in_host_memory = zero_copy;
         rc = tsvpp_convert_batch(ctx, dframes.data(), m, p, douts.data(), st);
+        ctx->frames_in_host_memory = false;
         if (rc) return rc;
         if (!zc_out)
             for (int k = 0; k < m; ++k)

@@ -77,6 +77,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
         : "memory");
 }
+// The same copy issued by ONE elected lane of a converged warp (all 32 lanes must execute this with
+// identical operands): an elect.sync predicate is known to be single-lane, so the copy goes straight
+// to the uniform datapath instead of through a loop over the active lanes.
+__device__ __forceinline__ void bulk_g2s_elected(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}"
+        ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -265,29 +277,39 @@ struct ItemIter {
     }
 };
 
-// One bulk copy per (output row of the strip, vertical tap).
+// One bulk copy per (output row of the strip, vertical tap).  Every operand of the copies is
+// warp-uniform (item coordinates, read-only table entries at uniform indices), so the copies are
+// issued from the uniform datapath by one lane without a per-lane serialisation loop.
 template <bool NEED_UV>
 __device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDev *__restrict__ frames,
                                                  const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane,
-                                                 uint64_t policy) {
-    const FrameDev fr = frames[ic.frame];
+                                                 uint64_t policy, int pwarp, int npwarps) {
+    const unsigned long long *fd = reinterpret_cast<const unsigned long long *>(frames + ic.frame);
+    const unsigned char *fy = reinterpret_cast<const unsigned char *>(__ldg(fd));
+    const unsigned char *fuv = reinterpret_cast<const unsigned char *>(__ldg(fd + 1));
     const int nl = 2 * P.rp * P.K;            // luma slots
     const int nc = NEED_UV ? P.rp * P.K : 0;  // chroma slots
-    const int a0l = P.seg_a0_l[ic.tile], lenl = P.seg_len_l[ic.tile];
-    const int a0c = NEED_UV ? P.seg_a0_c[ic.tile] : 0, lenc = NEED_UV ? P.seg_len_c[ic.tile] : 0;
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nl * lenl + nc * lenc));
-    __syncwarp();
+    const int a0l = __ldg(P.seg_a0_l + ic.tile), lenl = __ldg(P.seg_len_l + ic.tile);
+    const int a0c = NEED_UV ? __ldg(P.seg_a0_c + ic.tile) : 0, lenc = NEED_UV ? __ldg(P.seg_len_c + ic.tile) : 0;
     const int *rs_l = P.rowsrc_l + (size_t)ic.strip * nl;
-    for (int c = lane; c < nl; c += 32) {
-        const int row = rs_l[c];
-        bulk_g2s(stage + (size_t)c * P.slot_stride, fr.y + (size_t)row * P.pitch_y + a0l, lenl, bar, policy);
+    const int *rs_c = P.rowsrc_c + (size_t)ic.strip * nc;
+    // slots are dealt round-robin to the producer warps; each announces the bytes of its own copies
+    const int myl = (nl - pwarp + npwarps - 1) / npwarps, myc = (nc - pwarp + npwarps - 1) / npwarps;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(myl * lenl + myc * lenc));
+    __syncwarp();
+    fy += a0l;
+    fuv += a0c;
+#pragma unroll 4
+    for (int c = pwarp; c < nl; c += npwarps) {
+        const int row = __ldg(rs_l + c);
+        bulk_g2s_elected(stage + (size_t)c * P.slot_stride, fy + (size_t)row * P.pitch_y, lenl, bar, policy);
     }
     if (NEED_UV) {
-        const int *rs_c = P.rowsrc_c + (size_t)ic.strip * nc;
-        for (int c = lane; c < nc; c += 32) {
-            const int row = rs_c[c];
-            bulk_g2s(stage + (size_t)(nl + c) * P.slot_stride, fr.uv + (size_t)row * P.pitch_uv + a0c, lenc, bar,
-                     policy);
+        unsigned char *sc = stage + (size_t)nl * P.slot_stride;
+#pragma unroll 2
+        for (int c = pwarp; c < nc; c += npwarps) {
+            const int row = __ldg(rs_c + c);
+            bulk_g2s_elected(sc + (size_t)c * P.slot_stride, fuv + (size_t)row * P.pitch_uv, lenc, bar, policy);
         }
     }
 }
@@ -522,8 +544,8 @@ __device__ __forceinline__ void st_row_u8(unsigned char *dst, const uint32_t (&e
         if constexpr (NE % 4 == 0) {
             uint32_t w[NE / 4];
 #pragma unroll
-            for (int k = 0; k < NE / 4; ++k)
-                w[k] = e[4 * k] | (e[4 * k + 1] << 8) | (e[4 * k + 2] << 16) | (e[4 * k + 3] << 24);
+            for (int k = 0; k < NE / 4; ++k)  // three PRMTs per word
+                w[k] = __byte_perm(__byte_perm(e[4 * k], e[4 * k + 1], 0x0040), __byte_perm(e[4 * k + 2], e[4 * k + 3], 0x0040), 0x5410);
             st_words<NE / 4, 1>(dst, w);
         } else {  // NE == 2 or 6: 16-bit stores
 #pragma unroll
@@ -583,7 +605,12 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
         int C[2][BW][3];
 #pragma unroll
         for (int p = 0; p < BW / 2; ++p) {
-            const ChromaTerms t = chroma_terms(UV[p][0], UV[p][1]);
+            ChromaTerms t = chroma_terms(UV[p][0], UV[p][1]);
+            if (OK != OUT_HSV_F32 && P.swap_rb) {  // BGR: first channel is B (ColorConversion.cu:304-305);
+                const float tmp = t.r;              // swapping the two chroma terms once per pair swaps the
+                t.r = t.b;                          // R and B results of its four pixels
+                t.b = tmp;
+            }
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -599,16 +626,6 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
                 st_row_f32<3 * BW, BW>((float *)outp + ((size_t)(i0 + a) * dw + j0) * 3, e, full, 3 * nx);
             }
             return;
-        }
-        if (P.swap_rb) {  // BGR: first channel is B (ColorConversion.cu:304-305)
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < BW; ++b) {
-                    const int tmp = C[a][b][0];
-                    C[a][b][0] = C[a][b][2];
-                    C[a][b][2] = tmp;
-                }
         }
         if constexpr (OK == OUT_RGB_PLANAR_F32 || OK == OUT_RGB_PLANAR_U8) {
             const size_t plane = (size_t)dw * dh;
@@ -656,12 +673,19 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
     }
 }
 
+// BW consecutive staged bytes (BW-aligned) as one shared load
+template <int BW>
+__device__ __forceinline__ uint32_t ld_group(const unsigned char *p) {
+    if constexpr (BW == 4) return *reinterpret_cast<const uint32_t *>(p);
+    else return (uint32_t)*reinterpret_cast<const unsigned short *>(p);
+}
+
 // ---------------------------------------------------------------------------------------
 // The fused kernel.  blockDim.x = 32 (producer warp) + round_up(tw/BW * rp, 32) consumers;
 // every consumer thread owns a block of 2 rows x BW columns of the output.
 // ---------------------------------------------------------------------------------------
 template <int RS, int OK, bool BULK, int BW>
-__global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? 0 : 32 * (kLdgProducerWarps - 1)),
+__global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW == 4 ? 32 : 0) : 32 * (kLdgProducerWarps - 1)),
                                   BULK ? (BW == 4 ? 5 : ((RS == RS_BICUBIC || RS == RS_AREA) ? 3 : 4)) : 2)
     vpp_fused_kernel(const PlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
@@ -674,7 +698,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? 0 : 32
     unsigned char *stages = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * P.stage_bytes);
     uint64_t *empty = full + kMaxStages;
-    constexpr int NPROD = BULK ? 1 : kLdgProducerWarps;  // producer warps
+    const int NPROD = P.nprod;  // producer warps (bulk: 1, or 2 when the row segments are short; guarded loads: 4)
     const int ncons_warps = ((int)blockDim.x >> 5) - NPROD;
 
     const int total = nframes * P.nstrips * P.ntiles;
@@ -702,7 +726,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? 0 : 32
             mbar_wait(empty + s, phase);
             unsigned char *stage = stages + (size_t)s * P.stage_bytes;
             if (BULK)
-                issue_stage_bulk<NEED_UV>(P, frames, ic, stage, full + s, lane, policy);
+                issue_stage_bulk<NEED_UV>(P, frames, ic, stage, full + s, lane, policy, warp, NPROD);
             else
                 fill_stage_ldg<NEED_UV>(P, frames, ic, stage, full + s, lane, warp, NPROD);
             if (++s == NS) {
@@ -765,7 +789,29 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? 0 : 32
         for (int p = 0; p < BW / 2; ++p) UV[p][0] = UV[p][1] = 0;
         const int nx = min(BW, P.dw - j0), ny = min(2, P.dh - i0);
         const bool work = active && nx > 0 && ny > 0;
-        if (work) {
+        bool sampled = false;
+        if constexpr (RS == RS_NEAREST && SMALL_COL) {
+            // no horizontal resize: the block's bytes are consecutive and aligned in the staged rows
+            if (work && P.ident && nx == BW && ny == 2 && (!NEED_UV || (ci < P.ch2 && (j0 >> 1) + BW / 2 <= P.cw2))) {
+                const unsigned char *sl0 = stage + (size_t)(2 * ty) * P.slot_stride + lreg[0].o;
+                const uint32_t w0 = ld_group<BW>(sl0), w1 = ld_group<BW>(sl0 + P.slot_stride);
+#pragma unroll
+                for (int b = 0; b < BW; ++b) {
+                    Yv[0][b] = (int)__byte_perm(w0, 0u, 0x4440u + b);  // byte b, zero-extended: one PRMT
+                    Yv[1][b] = (int)__byte_perm(w1, 0u, 0x4440u + b);
+                }
+                if (NEED_UV) {
+                    const uint32_t wc = ld_group<BW>(stage + (size_t)(2 * P.rp + ty) * P.slot_stride + creg[0].o);
+#pragma unroll
+                    for (int p = 0; p < BW / 2; ++p) {
+                        UV[p][0] = (int)__byte_perm(wc, 0u, 0x4440u + 2 * p);
+                        UV[p][1] = (int)__byte_perm(wc, 0u, 0x4440u + 2 * p + 1);
+                    }
+                }
+                sampled = true;
+            }
+        }
+        if (work && !sampled) {
             const unsigned char *sl0 = stage + (size_t)((2 * ty) * P.K) * P.slot_stride;
             const unsigned char *sl1 = sl0 + (size_t)P.K * P.slot_stride;
 #pragma unroll
@@ -809,6 +855,101 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? 0 : 32
                 emit_block<OK, BW>(P, outp, i0, j0, Yv, UV, nx, ny, false);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Direct kernel: colour conversion / layout at the source size (the reference's default read():
+// no resize, optional crop).  Nothing is re-used between output blocks, so there is nothing to
+// stage: a warp takes 128 consecutive 2x4 blocks of a frame (row-major over blocks), every lane
+// owns blocks lane, lane+32, lane+64, lane+96 -- its three 32-bit loads per block (two luma rows,
+// one chroma row) and its stores are then contiguous across the warp.  All twelve loads of a lane
+// are issued before the first conversion.  Same arithmetic as the fused kernel (emit_block).
+// ---------------------------------------------------------------------------------------
+constexpr int kDirectSub = 4;  // blocks per lane
+template <int OK>
+__global__ void __launch_bounds__(256) vpp_direct_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
+                                                         int nframes, int vec_ok) {
+    constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
+    const int lane = threadIdx.x & 31;
+    const int ngx = P.dw >> 2, npr = P.dh >> 1;  // dw % 4 == 0, dh % 2 == 0 (plan)
+    const int upf = (ngx * npr + 32 * kDirectSub - 1) / (32 * kDirectSub);  // warp units per frame
+    const long u = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= (long)nframes * upf) return;
+    const int f = (int)(u / upf);
+    const int g0 = (int)(u - (long)f * upf) * (32 * kDirectSub) + lane;
+    const unsigned long long *fd = reinterpret_cast<const unsigned long long *>(frames + f);
+    const unsigned char *fy = reinterpret_cast<const unsigned char *>(__ldg(fd));
+    const unsigned char *fuv = reinterpret_cast<const unsigned char *>(__ldg(fd + 1));
+    void *outp = reinterpret_cast<void *>(__ldg(fd + 2));
+    fy += (size_t)P.d_row_l0 * P.pitch_y + P.d_x_l0;
+    fuv += (size_t)P.d_row_c0 * P.pitch_uv + P.d_x_c0;
+
+    int pr = g0 / ngx, gx = g0 - pr * ngx;
+    uint32_t w0[kDirectSub], w1[kDirectSub], wc[kDirectSub];
+    int prs[kDirectSub], gxs[kDirectSub];
+#pragma unroll
+    for (int k = 0; k < kDirectSub; ++k) {
+        prs[k] = pr;
+        gxs[k] = gx;
+        w0[k] = w1[k] = wc[k] = 0;
+        if (pr < npr) {
+            const unsigned char *ly = fy + (size_t)(2 * pr) * P.pitch_y + 4 * gx;
+            w0[k] = __ldcs(reinterpret_cast<const uint32_t *>(ly));
+            w1[k] = __ldcs(reinterpret_cast<const uint32_t *>(ly + P.pitch_y));
+            if (NEED_UV) wc[k] = __ldcs(reinterpret_cast<const uint32_t *>(fuv + (size_t)pr * P.pitch_uv + 4 * gx));
+        }
+        gx += 32;
+        while (gx >= ngx) {
+            gx -= ngx;
+            ++pr;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kDirectSub; ++k) {
+        if (prs[k] >= npr) continue;
+        int Yv[2][4], UV[2][2];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            Yv[0][b] = (int)__byte_perm(w0[k], 0u, 0x4440u + b);
+            Yv[1][b] = (int)__byte_perm(w1[k], 0u, 0x4440u + b);
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            UV[p][0] = (int)__byte_perm(wc[k], 0u, 0x4440u + 2 * p);
+            UV[p][1] = (int)__byte_perm(wc[k], 0u, 0x4440u + 2 * p + 1);
+        }
+        if (vec_ok)
+            emit_block<OK, 4>(P, outp, 2 * prs[k], 4 * gxs[k], Yv, UV, 4, 2, true);
+        else
+            emit_block<OK, 4>(P, outp, 2 * prs[k], 4 * gxs[k], Yv, UV, 4, 2, false);
+    }
+}
+
+using DirectFn = void (*)(const PlanDev, const FrameDev *, int, int);
+static DirectFn pick_direct(int ok) {
+    switch (ok) {
+        case OUT_RGB_PLANAR_U8: return vpp_direct_kernel<OUT_RGB_PLANAR_U8>;
+        case OUT_RGB_PLANAR_F32: return vpp_direct_kernel<OUT_RGB_PLANAR_F32>;
+        case OUT_RGB_MERGED_U8: return vpp_direct_kernel<OUT_RGB_MERGED_U8>;
+        case OUT_RGB_MERGED_F32: return vpp_direct_kernel<OUT_RGB_MERGED_F32>;
+        case OUT_Y800_U8: return vpp_direct_kernel<OUT_Y800_U8>;
+        case OUT_Y800_F32: return vpp_direct_kernel<OUT_Y800_F32>;
+        case OUT_HSV_F32: return vpp_direct_kernel<OUT_HSV_F32>;
+        case OUT_NV12_U8: return vpp_direct_kernel<OUT_NV12_U8>;
+        case OUT_NV12_F32: return vpp_direct_kernel<OUT_NV12_F32>;
+    }
+    return nullptr;
+}
+int launch_direct(int ok, const PlanDev &P, const FrameDev *frames_dev, int nframes, int vec_ok, cudaStream_t stream) {
+    DirectFn fn = pick_direct(ok);
+    if (!fn) return (int)cudaErrorMissingConfiguration;
+    const int ngx = P.dw >> 2, npr = P.dh >> 1;
+    const long upf = ((long)ngx * npr + 32 * kDirectSub - 1) / (32 * kDirectSub);
+    const long units = upf * nframes;
+    const long grid = (units + 7) / 8;
+    if (grid <= 0 || grid > 0x7fffffffL) return (int)cudaErrorInvalidConfiguration;
+    fn<<<(unsigned)grid, 256, 0, stream>>>(P, frames_dev, nframes, vec_ok);
+    return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------

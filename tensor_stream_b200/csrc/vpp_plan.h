@@ -69,7 +69,13 @@ struct PlanDev {
     long plane_bytes_y, plane_bytes_uv;  // extents for the guarded (non-bulk) fill
     int swap_rb;            // BGR
     int need_uv;            // 0 for Y800
+    int ident;              // nearest only: every aligned group of bw columns taps bw consecutive, bw-aligned staged
+                            // bytes (no horizontal resize): a thread reads its row of a block with one shared load
     int PX, PY;             // AREA pattern periods
+    // direct (unstaged) path: no resize, so source rows/columns are affine in the output coordinates
+    int direct;             // 1: the plan may run vpp_direct_kernel
+    int d_row_l0, d_row_c0; // source row of output luma row 0 / chroma row 0
+    int d_x_l0, d_x_c0;     // source byte of output column 0 in a luma / chroma row (multiples of 4)
     // tables (device pointers)
     const int *seg_a0_l;    // [ntiles] byte offset of the staged segment inside a luma row
     const int *seg_len_l;   // [ntiles] bytes (multiple of 16)
