@@ -182,10 +182,11 @@ __device__ __forceinline__ int bicubic_dot_fast(const float *cf, const double *c
 struct ChromaTerms {
     float r, g, b;
 };
-__device__ __forceinline__ ChromaTerms chroma_terms(int U, int V) {
+// `Um`, `Vm`: the samples as magic-float bits (kMagicBits | value)
+__device__ __forceinline__ ChromaTerms chroma_terms(uint32_t Um, uint32_t Vm) {
     // (float)(U-128): exact via the magic form with a folded bias (2^23 + 128)
-    const float fu = __fsub_rn(__uint_as_float(kMagicBits | (uint32_t)U), kMagic + 128.0f);
-    const float fv = __fsub_rn(__uint_as_float(kMagicBits | (uint32_t)V), kMagic + 128.0f);
+    const float fu = __fsub_rn(__uint_as_float(Um), kMagic + 128.0f);
+    const float fv = __fsub_rn(__uint_as_float(Vm), kMagic + 128.0f);
     ChromaTerms t;
     t.r = __fmaf_rn(fv, 1.5959997177f, 0.5f);
     t.b = __fmaf_rn(fu, 2.017999649f, 0.5f);
@@ -194,10 +195,10 @@ __device__ __forceinline__ ChromaTerms chroma_terms(int U, int V) {
     t.g = __fadd_rn(g, 0.5f);
     return t;
 }
-// one pixel -> the three channels, each already clamped to 0..255
-__device__ __forceinline__ void yuv_px_bits(int Y, const ChromaTerms &t, int &R, int &G, int &B) {
-    // max(0, Y-16) on integers first: identical to max(0.f, (float)Y - 16.f)
-    const float yp = u2f((uint32_t)max(Y - 16, 0));
+// one pixel -> the three channels, each already clamped to 0..255.  `Ym` = kMagicBits | Y.
+__device__ __forceinline__ void yuv_px_bits(uint32_t Ym, const ChromaTerms &t, int &R, int &G, int &B) {
+    // max(0.f, (float)Y - 16.f): (2^23 + Y) - (2^23 + 16) is exact, one FADD on the FMA pipe
+    const float yp = fmaxf(__fsub_rn(__uint_as_float(Ym), kMagic + 16.0f), 0.0f);
     R = (int)f2u8_sat(__fmaf_rn(yp, 1.163999557f, t.r));
     G = (int)f2u8_sat(__fmaf_rn(yp, 1.163999557f, t.g));
     B = (int)f2u8_sat(__fmaf_rn(yp, 1.163999557f, t.b));
@@ -537,6 +538,16 @@ __device__ __forceinline__ void st_row_f32(float *dst, const float (&e)[NE], boo
         for (int k = 0; k < nvalid; ++k) dst[k] = e[k];
     }
 }
+// b0 | b1<<8 | b2<<16 | b3<<24 for clean bytes, as integer multiply-adds
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    uint32_t w;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "mad.lo.u32 t, %2, 256, %1;\n\t"
+        "mad.lo.u32 t, %3, 65536, t;\n\t"
+        "mad.lo.u32 %0, %4, 16777216, t;\n\t}"
+        : "=r"(w) : "r"(b0), "r"(b1), "r"(b2), "r"(b3));
+    return w;
+}
 // one row segment of NE byte elements (values 0..255 in uint32)
 template <int NE, int BW>
 __device__ __forceinline__ void st_row_u8(unsigned char *dst, const uint32_t (&e)[NE], bool full, int nvalid) {
@@ -544,8 +555,8 @@ __device__ __forceinline__ void st_row_u8(unsigned char *dst, const uint32_t (&e
         if constexpr (NE % 4 == 0) {
             uint32_t w[NE / 4];
 #pragma unroll
-            for (int k = 0; k < NE / 4; ++k)  // three PRMTs per word
-                w[k] = __byte_perm(__byte_perm(e[4 * k], e[4 * k + 1], 0x0040), __byte_perm(e[4 * k + 2], e[4 * k + 3], 0x0040), 0x5410);
+            for (int k = 0; k < NE / 4; ++k)  // three multiply-adds per word: the FMA pipe has the headroom, the ALU pipe not
+                w[k] = pack4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
             st_words<NE / 4, 1>(dst, w);
         } else {  // NE == 2 or 6: 16-bit stores
 #pragma unroll
@@ -560,7 +571,8 @@ __device__ __forceinline__ void st_row_u8(unsigned char *dst, const uint32_t (&e
 // Yv[a][b]: resized luma of pixel (i0+a, j0+b); UV[p] = {U,V} of column pair p (0 if it does not
 // exist).  nx, ny: how many columns/rows of the block lie inside the image; full: nx==BW && ny==2
 // and the vector-store alignment conditions hold.
-template <int OK, int BW>
+// MAGIC: Yv / UV already hold kMagicBits | value (RGB-family outputs only)
+template <int OK, int BW, bool MAGIC = false>
 __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0, int j0, const int (&Yv)[2][BW],
                                            const int (&UV)[BW / 2][2], int nx, int ny, bool full) {
     const int dw = P.dw, dh = P.dh;
@@ -605,7 +617,8 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
         int C[2][BW][3];
 #pragma unroll
         for (int p = 0; p < BW / 2; ++p) {
-            ChromaTerms t = chroma_terms(UV[p][0], UV[p][1]);
+            ChromaTerms t = chroma_terms(MAGIC ? (uint32_t)UV[p][0] : (kMagicBits | (uint32_t)UV[p][0]),
+                                         MAGIC ? (uint32_t)UV[p][1] : (kMagicBits | (uint32_t)UV[p][1]));
             if (OK != OUT_HSV_F32 && P.swap_rb) {  // BGR: first channel is B (ColorConversion.cu:304-305);
                 const float tmp = t.r;              // swapping the two chroma terms once per pair swaps the
                 t.r = t.b;                          // R and B results of its four pixels
@@ -614,7 +627,9 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) yuv_px_bits(Yv[a][2 * p + b], t, C[a][2 * p + b][0], C[a][2 * p + b][1], C[a][2 * p + b][2]);
+                for (int b = 0; b < 2; ++b)
+                    yuv_px_bits(MAGIC ? (uint32_t)Yv[a][2 * p + b] : (kMagicBits | (uint32_t)Yv[a][2 * p + b]), t,
+                                C[a][2 * p + b][0], C[a][2 * p + b][1], C[a][2 * p + b][2]);
         }
         if constexpr (OK == OUT_HSV_F32) {
             // reference src/ColorConversion.cu:360-372: from normalised RGB (never BGR), merged
@@ -907,21 +922,25 @@ __global__ void __launch_bounds__(256) vpp_direct_kernel(const PlanDev P, const 
 #pragma unroll
     for (int k = 0; k < kDirectSub; ++k) {
         if (prs[k] >= npr) continue;
+        // RGB family: one PRMT per sample builds kMagicBits | byte (the float 2^23 + value) directly
+        constexpr bool MAGIC = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32 || OK == OUT_NV12_U8 || OK == OUT_NV12_F32);
+        constexpr uint32_t hi = MAGIC ? kMagicBits : 0u;
+        constexpr uint32_t sel = MAGIC ? 0x7540u : 0x4440u;  // bytes {src b, 0, 0, 0x4B} / {src b, 0, 0, 0}
         int Yv[2][4], UV[2][2];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            Yv[0][b] = (int)__byte_perm(w0[k], 0u, 0x4440u + b);
-            Yv[1][b] = (int)__byte_perm(w1[k], 0u, 0x4440u + b);
+            Yv[0][b] = (int)__byte_perm(w0[k], hi, sel + b);
+            Yv[1][b] = (int)__byte_perm(w1[k], hi, sel + b);
         }
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            UV[p][0] = (int)__byte_perm(wc[k], 0u, 0x4440u + 2 * p);
-            UV[p][1] = (int)__byte_perm(wc[k], 0u, 0x4440u + 2 * p + 1);
+            UV[p][0] = (int)__byte_perm(wc[k], hi, sel + 2 * p);
+            UV[p][1] = (int)__byte_perm(wc[k], hi, sel + 2 * p + 1);
         }
         if (vec_ok)
-            emit_block<OK, 4>(P, outp, 2 * prs[k], 4 * gxs[k], Yv, UV, 4, 2, true);
+            emit_block<OK, 4, MAGIC>(P, outp, 2 * prs[k], 4 * gxs[k], Yv, UV, 4, 2, true);
         else
-            emit_block<OK, 4>(P, outp, 2 * prs[k], 4 * gxs[k], Yv, UV, 4, 2, false);
+            emit_block<OK, 4, MAGIC>(P, outp, 2 * prs[k], 4 * gxs[k], Yv, UV, 4, 2, false);
     }
 }
 
