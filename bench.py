@@ -277,12 +277,16 @@ def run_ours(args):
 
     # ---- end to end: host buffers through the C ABI (H2D + kernel + D2H inside the call) ----
     ne = args.e2e_frames
-    hy = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
-    huv = [torch.empty((H // 2, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
-    for i in range(ne):
-        hy[i].copy_(ys[i % n])
-        huv[i].copy_(uvs[i % n])
-    hout = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(ne)]
+    # pinned host buffers on the GPU's own NUMA node (tensor_stream_b200/numa.py: in-place reads from
+    # the other socket run at a quarter of the PCIe rate); the reference arm allocates the same way
+    from tensor_stream_b200 import numa
+    with numa.bound_to_gpu(dev.index) as numa_node:
+        hy = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
+        huv = [torch.empty((H // 2, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
+        for i in range(ne):
+            hy[i].copy_(ys[i % n])
+            huv[i].copy_(uvs[i % n])
+        hout = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(ne)]
     hframes = list(zip(hy, huv))
     e2e_steps = max(3, min(args.steps, 10))
     fetch = int(plan.split("fetch_bytes_per_frame=")[1].split()[0]) if "fetch_bytes_per_frame=" in plan else None
@@ -338,7 +342,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": ne * (fetch if (best_mode == "zero_copy" and fetch) else W * H * 3 // 2),
                 "d2h_bytes_per_step": ne * DW * DH * 3 * 4, "frames_per_step": ne, "steps": e2e_steps,
                 "api": "tsvpp_convert_batch_host (pinned host NV12 in, host float32 out)",
-                "path": best_mode,
+                "path": best_mode, "host_buffers_numa_node": numa_node,
                 "zero_copy_fps": world * ne * e2e_steps / (e2e_zc_ms * 1e-3),
                 "staged_h2d_fps": world * ne * e2e_steps / (e2e_st_ms * 1e-3),
                 "note": "zero_copy: the fused kernel reads the pinned host frames in place, so only the source rows its "
@@ -433,11 +437,13 @@ def run_reference(args):
 
     # end to end with host buffers: H2D of the frame, Convert, D2H of the result, per frame
     ne = args.e2e_frames
-    hy = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
-    huv = [torch.empty((H // 2, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
-    for i in range(ne):
-        hy[i].copy_(ys[i % n])
-        huv[i].copy_(uvs[i % n])
+    from tensor_stream_b200 import numa
+    with numa.bound_to_gpu(dev.index) as numa_node:  # same host-memory placement as our arm
+        hy = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
+        huv = [torch.empty((H // 2, W), dtype=torch.uint8).pin_memory() for _ in range(ne)]
+        for i in range(ne):
+            hy[i].copy_(ys[i % n])
+            huv[i].copy_(uvs[i % n])
     dy = torch.empty((H, W), dtype=torch.uint8, device=dev)
     duv = torch.empty((H // 2, W), dtype=torch.uint8, device=dev)
     hout = np.empty(DW * DH * 3, dtype=np.float32)
@@ -471,7 +477,8 @@ def run_reference(args):
                    "ranks_running": 1, "requested_gpus": args.gpus},
         "e2e": {"value": e2e_fps, "unit": "frames/sec", "h2d_bytes_per_step": ne * W * H * 3 // 2,
                 "d2h_bytes_per_step": ne * DW * DH * 3 * 4, "frames_per_step": ne, "steps": e2e_steps,
-                "api": "cudaMemcpy H2D + VideoProcessor::Convert + cudaMemcpy D2H per frame"},
+                "api": "cudaMemcpy H2D + VideoProcessor::Convert + cudaMemcpy D2H per frame",
+                "host_buffers_numa_node": numa_node},
         "cpu_baseline": {"value": fps, "unit": "frames/sec", "cores": nthreads, "kind": "reference",
                          "sample": "GPU reference driven by %d host threads; %d frames x %d steps" % (nthreads, n, args.steps)},
         "clocks": clocks,

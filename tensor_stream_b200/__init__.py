@@ -7,4 +7,5 @@ The native library (tensor_stream_b200/libtsvpp.so) is loaded on first use; ther
 """
 from .vpp import (FourCC, FrameParameters, Planes, ResizeType, VideoProcessor, VppError,  # noqa: F401
                   convert_batch_aten, load_library, output_info, output_shape)
+from . import numa  # noqa: F401  (host-memory placement for the zero-copy host path)
 from .stream import FrameRate, LogsLevel, LogsType, StatusLevel, TensorStreamConverter  # noqa: F401

@@ -206,3 +206,30 @@ def test_c_abi_header_is_plain_c(lib, tmp_path):
     probe = C.CDLL(str(so)).probe
     probe.restype = C.c_int
     assert probe() == 0 + 3 * 256 * 256 + 256 + 256 + 4
+
+
+def test_numa_binding_uses_the_gpu_node_cpus(tmp_path, monkeypatch):
+    """tensor_stream_b200/numa.py: pinned buffers for the zero-copy host path are allocated with the
+    thread bound to the GPU's NUMA node; the affinity is restored afterwards and nothing happens when
+    the topology is unknown."""
+    import os
+    from tensor_stream_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    mine = sorted(os.sched_getaffinity(0))
+    pick = mine[: max(1, len(mine) // 2)]
+    sysfs = tmp_path
+    (sysfs / "bus/pci/devices/0000:d1:00.0").mkdir(parents=True)
+    (sysfs / "bus/pci/devices/0000:d1:00.0/numa_node").write_text("1\n")
+    (sysfs / "devices/system/node/node1").mkdir(parents=True)
+    (sysfs / "devices/system/node/node1/cpulist").write_text(",".join(str(c) for c in pick) + "\n")
+    monkeypatch.setattr(numa, "gpu_pci_bus_id", lambda index: "0000:d1:00.0")
+    assert numa.gpu_numa_node(0, str(sysfs)) == 1
+    with numa.bound_to_gpu(0, str(sysfs)) as node:
+        assert node == 1
+        assert os.sched_getaffinity(0) == set(pick)
+    assert sorted(os.sched_getaffinity(0)) == mine
+    # unknown topology (numa_node = -1, as in VMs) -> no-op
+    (sysfs / "bus/pci/devices/0000:d1:00.0/numa_node").write_text("-1\n")
+    with numa.bound_to_gpu(0, str(sysfs)) as node:
+        assert node is None
+        assert sorted(os.sched_getaffinity(0)) == mine

@@ -357,6 +357,60 @@ def test_exhaustive_yuv_to_rgb(vp):
     assert _same(got, want), _diff_report(got, want)
 
 
+NORESIZE_KINDS = [
+    ("rgb_merged_u8", dict(fourcc=G.RGB24)),
+    ("bgr_merged_f32", dict(fourcc=G.BGR24, normalization=True)),
+    ("rgb_planar_u8", dict(fourcc=G.RGB24, planes=G.PLANAR)),
+    ("bgr_planar_f32", dict(fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
+    ("y800_u8", dict(fourcc=G.Y800)),
+    ("y800_f32", dict(fourcc=G.Y800, normalization=True)),
+    ("hsv", dict(fourcc=G.HSV)),
+    ("nv12_u8", dict(fourcc=G.NV12)),
+    ("nv12_f32", dict(fourcc=G.NV12, normalization=True)),
+]
+NORESIZE_GEOM = [
+    # name, w, h, pitch, crop, takes the direct kernel?
+    ("full_1000x502_pitch1024", 1000, 502, 1024, None, True),     # 250 blocks per row: units straddle rows
+    ("crop_x0_8", 1280, 720, 1280, (8, 6, 648, 486), True),
+    ("crop_x0_6_staged", 1280, 720, 1280, (6, 6, 646, 486), False),  # crop origin not 4-byte aligned
+    ("width_not_multiple_of_4_staged", 1282, 720, 1296, None, False),
+    ("narrow_12x4", 64, 48, 64, (16, 8, 28, 12), True),            # fewer than 32 blocks per row
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gname,w,h,pitch,crop,direct", NORESIZE_GEOM, ids=[g[0] for g in NORESIZE_GEOM])
+def test_noresize_direct_and_staged_kernels_agree_with_the_oracle(vp, gname, w, h, pitch, crop, direct):
+    """The unstaged kernel (vpp_direct_kernel) and the staged fused kernel are two executions of the
+    same arithmetic; both must reproduce the oracle for every output kind, and the plan must pick the
+    direct kernel exactly when its alignment conditions hold."""
+    from tensor_stream_b200 import vpp
+    y, uv = _synthetic(w, h, seed=zlib.crc32(gname.encode()))
+    ty, tuv, _ = _to_dev(y, uv, pitch)
+    os.environ["TSVPP_NO_DIRECT"] = "1"
+    try:
+        staged = vpp.VideoProcessor(0)  # plans are built (and cached) per processor
+        for kname, kw in NORESIZE_KINDS:
+            kw = dict(kw)
+            if crop:
+                kw["crop"] = crop
+            want = _run_oracle(y, uv, kw)
+            assert "direct=0" in staged.describe_plan(ty, tuv, _params(kw), width=w, height=h)
+            got_s = staged.convert(ty, tuv, _params(kw), width=w, height=h).cpu().numpy().reshape(-1)
+            assert _same(got_s, want), kname + " staged: " + _diff_report(got_s, want)
+            os.environ.pop("TSVPP_NO_DIRECT")
+            try:
+                desc = vp.describe_plan(ty, tuv, _params(kw), width=w, height=h)
+                assert ("direct=1" in desc) == direct, desc
+                got_d = vp.convert(ty, tuv, _params(kw), width=w, height=h).cpu().numpy().reshape(-1)
+            finally:
+                os.environ["TSVPP_NO_DIRECT"] = "1"
+            assert _same(got_d, want), kname + " direct: " + _diff_report(got_d, want)
+        staged.close()
+    finally:
+        os.environ.pop("TSVPP_NO_DIRECT", None)
+
+
 def test_error_codes_match_the_reference_contract(vp):
     """Status codes of the boundary: 0, the reference's Internal enum, or a positive cudaError_t
     (include/Common.h:19-24, src/ColorConversion.cu:376)."""
