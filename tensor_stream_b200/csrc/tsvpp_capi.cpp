@@ -738,6 +738,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     pl->out_w = dw;
     pl->out_h = dh;
     pl->out_elems = (size_t)(channels_of(p.fourcc) * dw * dh);
+    if ((double)channels_of(p.fourcc) * dw * dh >= 4294967296.0) return TSVPP_UNSUPPORTED;  // 32-bit element offsets
     pl->elem_size = (p.normalization || p.fourcc == TSVPP_HSV) ? 4 : 1;
     pl->vec_ok_geom = (dw % bw == 0) ? 1 : 0;
     // bytes one frame's work items fetch from the source planes (what crosses HBM / PCIe)

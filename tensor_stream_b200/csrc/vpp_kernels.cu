@@ -371,6 +371,30 @@ __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev 
 // ---------------------------------------------------------------------------------------
 // Resampling of one output sample (one byte of the reference's resized NV12 image)
 // ---------------------------------------------------------------------------------------
+// The dynamic shared memory (stage ring + mbarriers) of the fused kernel.
+extern __shared__ __align__(128) unsigned char smem[];
+
+// A position inside `smem` as a 32-bit shared-space address.  The consumers derive every tap address
+// from one laundered base register and load with ld.shared: with `unsigned char *` (or `smem[i]`)
+// arithmetic the compiler re-materialised the address of `smem` (S2UR SR_CgaCtaId / UMOV / ULEA /
+// IMAD.U32) in every basic block of the sampling code -- four extra instructions per block, the ULEA
+// among the top stall sites of the bilinear kernels.
+struct SPtr {
+    uint32_t addr;
+    __device__ __forceinline__ SPtr operator+(int d) const { return SPtr{addr + (uint32_t)d}; }
+    __device__ __forceinline__ uint32_t operator[](int i) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)i));
+        return v;
+    }
+};
+// shared-space address of smem[0], opaque to the optimiser so that it stays in one register
+__device__ __forceinline__ uint32_t smem_base_laundered() {
+    uint32_t b = smem_addr(smem);
+    asm volatile("" : "+r"(b));
+    return b;
+}
+
 template <int RS>
 struct ColOf;
 template <>
@@ -386,14 +410,14 @@ struct ColOf<RS_AREA> { using T = ColArea; };
 // in registers, the taps are immediate-offset shared loads.  Summation order and rounding are the
 // reference's (rows outer, columns inner; w = px*py; sum = fma(d, w, sum)).
 template <int KXT, int STRIDE>
-__device__ __noinline__ int area_sample(const unsigned char *s0, int slot_stride, int K, const float *__restrict__ px,
+__device__ __noinline__ int area_sample(SPtr s0, int slot_stride, int K, const float *__restrict__ px,
                                         const float *__restrict__ py, float div) {
     float pxr[KXT];
 #pragma unroll
     for (int b = 0; b < KXT; ++b) pxr[b] = __ldg(px + b);
     float sum = 0.0f;
     for (int a = 0; a < K; ++a) {
-        const unsigned char *s = s0 + a * slot_stride;
+        const SPtr s = s0 + a * slot_stride;
         const float wyv = __ldg(py + a);
 #pragma unroll
         for (int b = 0; b < KXT; ++b) sum = __fmaf_rn(u2f(s[b * STRIDE]), __fmul_rn(pxr[b], wyv), sum);
@@ -406,12 +430,12 @@ __device__ __noinline__ int area_sample(const unsigned char *s0, int slot_stride
 // at the chroma index, src/Resize.cu:303-310), `stride` is 1 for luma and 2 for chroma bytes,
 // `wy` is the preloaded bilinear vertical weight.
 template <int RS>
-__device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *slots,
+__device__ __forceinline__ int resample(const PlanDev &P, SPtr slots,
                                         const typename ColOf<RS>::T &col, int orow, int stride, float wy) {
     if constexpr (RS == RS_NEAREST) {
         return slots[col.o];
     } else if constexpr (RS == RS_BILINEAR) {
-        const unsigned char *s0 = slots, *s1 = slots + P.slot_stride;
+        const SPtr s0 = slots, s1 = slots + P.slot_stride;
         return bilinear_px(s0[col.o0], s0[col.o1], s1[col.o0], s1[col.o1], col.w, wy);
     } else if constexpr (RS == RS_BICUBIC) {
         const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
@@ -420,7 +444,7 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
         uint32_t b[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const unsigned char *s = slots + k * P.slot_stride;
+            const SPtr s = slots + k * P.slot_stride;
             b[k] = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
         }
         const float4 cyf4 = __ldg(reinterpret_cast<const float4 *>(P.cyf) + orow);
@@ -433,7 +457,7 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
         const int prow_y = orow % P.PY;
         const float *py = P.py + (size_t)prow_y * P.K;
         const float div = __ldg(P.area_div + (size_t)prow_y * P.PX + col.prow);
-        const unsigned char *s0 = slots + col.o;
+        const SPtr s0 = slots + col.o;
         if (stride == 1) {
             switch (P.KX) {
                 case 2: return area_sample<2, 1>(s0, P.slot_stride, P.K, px, py, div);
@@ -459,7 +483,7 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
         }
         float sum = 0.0f;  // generic window width
         for (int a = 0; a < P.K; ++a) {
-            const unsigned char *s = s0 + a * P.slot_stride;
+            const SPtr s = s0 + a * P.slot_stride;
             const float wyv = __ldg(py + a);
             for (int b = 0; b < P.KX; ++b) sum = __fmaf_rn(u2f(s[b * stride]), __fmul_rn(__ldg(px + b), wyv), sum);
         }
@@ -471,7 +495,7 @@ __device__ __forceinline__ int resample(const PlanDev &P, const unsigned char *s
 // wherever the two rows tap the same source row (`shift`, warp-uniform, from the plan): the sum
 // depends on (source row, column) only, so this is the reference's arithmetic evaluated once
 // instead of twice.
-__device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, const unsigned char *sl0, const unsigned char *sl1,
+__device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, SPtr sl0, SPtr sl1,
                                                   const ColBicubic &col, int i0, int shift, bool two_rows, int &y0,
                                                   int &y1) {
     const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
@@ -480,7 +504,7 @@ __device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, const unsign
     uint32_t b0[4], b1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const unsigned char *s = sl0 + k * P.slot_stride;
+        const SPtr s = sl0 + k * P.slot_stride;
         b0[k] = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
     }
     {
@@ -500,7 +524,7 @@ __device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, const unsign
         else if (shift == 2 && k <= 1) { reuse = true; v = b0[k + 2 > 3 ? 3 : k + 2]; }
         else if (shift == 3 && k == 0) { reuse = true; v = b0[3]; }
         if (!reuse) {
-            const unsigned char *s = sl1 + k * P.slot_stride;
+            const SPtr s = sl1 + k * P.slot_stride;
             v = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
         }
         b1[k] = v;
@@ -574,7 +598,9 @@ __device__ __forceinline__ void st_row_u8(unsigned char *dst, const uint32_t (&e
 // Yv[a][b]: resized luma of pixel (i0+a, j0+b); UV[p] = {U,V} of column pair p (0 if it does not
 // exist).  nx, ny: how many columns/rows of the block lie inside the image; full: nx==BW && ny==2
 // and the vector-store alignment conditions hold.
-// MAGIC: Yv / UV already hold kMagicBits | value (RGB-family outputs only)
+// MAGIC: Yv / UV already hold kMagicBits | value (RGB-family outputs only).
+// Element offsets are 32-bit (the plan refuses outputs of 2^32 elements or more): one IMAD.WIDE per store
+// address instead of a 64-bit multiply chain.
 template <int OK, int BW, bool MAGIC = false>
 __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0, int j0, const int (&Yv)[2][BW],
                                            const int (&UV)[BW / 2][2], int nx, int ny, bool full) {
@@ -586,7 +612,7 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
             uint32_t e[BW];
 #pragma unroll
             for (int b = 0; b < BW; ++b) e[b] = (uint32_t)Yv[a][b];
-            st_row_u8<BW, BW>(o + (size_t)(i0 + a) * dw + j0, e, full, nx);
+            st_row_u8<BW, BW>(o + ((uint32_t)(i0 + a) * (uint32_t)dw + (uint32_t)j0), e, full, nx);
         }
         if constexpr (OK == OUT_NV12_U8) {
             // reference src/ColorConversion.cu:211-233 (NV12MergeBuffers): Y plane then UV plane
@@ -595,7 +621,7 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
 #pragma unroll
                 for (int p = 0; p < BW / 2; ++p) { e[2 * p] = (uint32_t)UV[p][0]; e[2 * p + 1] = (uint32_t)UV[p][1]; }
                 const int nuv = 2 * max(0, min(BW / 2, P.cw2 - (j0 >> 1)));
-                st_row_u8<BW, BW>(o + (size_t)dw * dh + (size_t)(i0 >> 1) * dw + j0, e, full && nuv == BW, nuv);
+                st_row_u8<BW, BW>(o + ((uint32_t)dw * (uint32_t)dh + (uint32_t)(i0 >> 1) * (uint32_t)dw + (uint32_t)j0), e, full && nuv == BW, nuv);
             }
         }
     } else if constexpr (OK == OUT_Y800_F32 || OK == OUT_NV12_F32) {
@@ -604,7 +630,7 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
             float e[BW];
 #pragma unroll
             for (int b = 0; b < BW; ++b) e[b] = div255_u8((uint32_t)Yv[a][b]);
-            st_row_f32<BW, BW>(o + (size_t)(i0 + a) * dw + j0, e, full, nx);
+            st_row_f32<BW, BW>(o + ((uint32_t)(i0 + a) * (uint32_t)dw + (uint32_t)j0), e, full, nx);
         }
         if constexpr (OK == OUT_NV12_F32) {
             if ((i0 >> 1) < P.ch2) {
@@ -612,7 +638,7 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
 #pragma unroll
                 for (int p = 0; p < BW / 2; ++p) { e[2 * p] = div255_u8((uint32_t)UV[p][0]); e[2 * p + 1] = div255_u8((uint32_t)UV[p][1]); }
                 const int nuv = 2 * max(0, min(BW / 2, P.cw2 - (j0 >> 1)));
-                st_row_f32<BW, BW>(o + (size_t)dw * dh + (size_t)(i0 >> 1) * dw + j0, e, full && nuv == BW, nuv);
+                st_row_f32<BW, BW>(o + ((uint32_t)dw * (uint32_t)dh + (uint32_t)(i0 >> 1) * (uint32_t)dw + (uint32_t)j0), e, full && nuv == BW, nuv);
             }
         }
     } else {
@@ -641,32 +667,32 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
 #pragma unroll
                 for (int b = 0; b < BW; ++b)
                     rgb_to_hsv(div255_bits(C[a][b][0]), div255_bits(C[a][b][1]), div255_bits(C[a][b][2]), e[3 * b], e[3 * b + 1], e[3 * b + 2]);
-                st_row_f32<3 * BW, BW>((float *)outp + ((size_t)(i0 + a) * dw + j0) * 3, e, full, 3 * nx);
+                st_row_f32<3 * BW, BW>((float *)outp + ((uint32_t)(i0 + a) * (uint32_t)dw + (uint32_t)j0) * 3u, e, full, 3 * nx);
             }
             return;
         }
         if constexpr (OK == OUT_RGB_PLANAR_F32 || OK == OUT_RGB_PLANAR_U8) {
-            const size_t plane = (size_t)dw * dh;
+            const uint32_t plane = (uint32_t)dw * (uint32_t)dh;
             for (int a = 0; a < nrow; ++a) {
-                const size_t off = (size_t)(i0 + a) * dw + j0;
+                const uint32_t off = (uint32_t)(i0 + a) * (uint32_t)dw + (uint32_t)j0;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     if constexpr (OK == OUT_RGB_PLANAR_F32) {
                         float e[BW];
 #pragma unroll
                         for (int b = 0; b < BW; ++b) e[b] = div255_bits(C[a][b][ch]);
-                        st_row_f32<BW, BW>((float *)outp + ch * plane + off, e, full, nx);
+                        st_row_f32<BW, BW>((float *)outp + ((uint32_t)ch * plane + off), e, full, nx);
                     } else {
                         uint32_t e[BW];
 #pragma unroll
                         for (int b = 0; b < BW; ++b) e[b] = bits_u8(C[a][b][ch]);
-                        st_row_u8<BW, BW>((unsigned char *)outp + ch * plane + off, e, full, nx);
+                        st_row_u8<BW, BW>((unsigned char *)outp + ((uint32_t)ch * plane + off), e, full, nx);
                     }
                 }
             }
         } else {
             for (int a = 0; a < nrow; ++a) {
-                const size_t off = ((size_t)(i0 + a) * dw + j0) * 3;
+                const uint32_t off = ((uint32_t)(i0 + a) * (uint32_t)dw + (uint32_t)j0) * 3u;
                 if constexpr (OK == OUT_RGB_MERGED_F32) {
                     float e[3 * BW];
 #pragma unroll
@@ -693,9 +719,30 @@ __device__ __forceinline__ void emit_block(const PlanDev &P, void *outp, int i0,
 
 // BW consecutive staged bytes (BW-aligned) as one shared load
 template <int BW>
-__device__ __forceinline__ uint32_t ld_group(const unsigned char *p) {
-    if constexpr (BW == 4) return *reinterpret_cast<const uint32_t *>(p);
-    else return (uint32_t)*reinterpret_cast<const unsigned short *>(p);
+__device__ __forceinline__ uint32_t ld_group(SPtr p) {
+    uint32_t v;
+    if constexpr (BW == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p.addr));
+    else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(p.addr));
+    return v;
+}
+
+// one column-parameter record (4, 8 or 16 bytes, naturally aligned in the plan tables) as one load
+template <class T>
+__device__ __forceinline__ T ld_col(const T *p) {
+    T t;
+    if constexpr (sizeof(T) == 16) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+        memcpy(&t, &v, sizeof(T));
+    } else if constexpr (sizeof(T) == 8) {
+        const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+        memcpy(&t, &v, sizeof(T));
+    } else if constexpr (sizeof(T) == 4) {
+        const int v = __ldg(reinterpret_cast<const int *>(p));
+        memcpy(&t, &v, sizeof(T));
+    } else {
+        t = *p;
+    }
+    return t;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -709,8 +756,6 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     using ColT = typename ColOf<RS>::T;
     constexpr bool SMALL_COL = sizeof(ColT) <= 16;
-    extern __shared__ __align__(128) unsigned char smem[];
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NS = P.nstages;
     unsigned char *stages = smem;
@@ -765,6 +810,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
     const ColT *col_l = reinterpret_cast<const ColT *>(P.col_l);
     const ColT *col_c = reinterpret_cast<const ColT *>(P.col_c);
 
+    const uint32_t sbase = smem_base_laundered();
     int cur_tile = -1;
     ColT lreg[BW], creg[BW];  // column parameters (kept in registers when small)
 
@@ -773,7 +819,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
     int s = 0;
     uint32_t phase = 0;
     for (int it = 0; it < my_items; ++it, ic.next(P)) {
-        const unsigned char *stage = stages + (size_t)s * P.stage_bytes;
+        const SPtr stage{sbase + (uint32_t)(s * P.stage_bytes)};
         const int colbase = ic.tile * P.tw + BW * tx;
         const int i0 = (ic.strip * P.rp + ty) * 2;  // first output row of this thread's block
         const int ci = ic.strip * P.rp + ty;        // its chroma row
@@ -784,8 +830,8 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
             if (SMALL_COL && ic.tile != cur_tile) {
 #pragma unroll
                 for (int b = 0; b < BW; ++b) {
-                    lreg[b] = col_l[colbase + b];
-                    if (NEED_UV) creg[b] = col_c[colbase + b];
+                    lreg[b] = ld_col(col_l + colbase + b);
+                    if (NEED_UV) creg[b] = ld_col(col_c + colbase + b);
                 }
                 cur_tile = ic.tile;
             }
@@ -811,7 +857,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
         if constexpr (RS == RS_NEAREST && SMALL_COL) {
             // no horizontal resize: the block's bytes are consecutive and aligned in the staged rows
             if (work && P.ident && nx == BW && ny == 2 && (!NEED_UV || (ci < P.ch2 && (j0 >> 1) + BW / 2 <= P.cw2))) {
-                const unsigned char *sl0 = stage + (size_t)(2 * ty) * P.slot_stride + lreg[0].o;
+                const SPtr sl0 = stage + ((2 * ty) * P.slot_stride + lreg[0].o);
                 const uint32_t w0 = ld_group<BW>(sl0), w1 = ld_group<BW>(sl0 + P.slot_stride);
 #pragma unroll
                 for (int b = 0; b < BW; ++b) {
@@ -819,7 +865,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
                     Yv[1][b] = (int)__byte_perm(w1, 0u, 0x4440u + b);
                 }
                 if (NEED_UV) {
-                    const uint32_t wc = ld_group<BW>(stage + (size_t)(2 * P.rp + ty) * P.slot_stride + creg[0].o);
+                    const uint32_t wc = ld_group<BW>(stage + ((2 * P.rp + ty) * P.slot_stride + creg[0].o));
 #pragma unroll
                     for (int p = 0; p < BW / 2; ++p) {
                         UV[p][0] = (int)__byte_perm(wc, 0u, 0x4440u + 2 * p);
@@ -830,8 +876,8 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
             }
         }
         if (work && !sampled) {
-            const unsigned char *sl0 = stage + (size_t)((2 * ty) * P.K) * P.slot_stride;
-            const unsigned char *sl1 = sl0 + (size_t)P.K * P.slot_stride;
+            const SPtr sl0 = stage + (2 * ty) * P.K * P.slot_stride;
+            const SPtr sl1 = sl0 + P.K * P.slot_stride;
 #pragma unroll
             for (int b = 0; b < BW; ++b) {
                 if (b < nx) {
@@ -845,7 +891,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
                 }
             }
             if (NEED_UV && ci < P.ch2) {
-                const unsigned char *sc = stage + (size_t)((2 * P.rp + ty) * P.K) * P.slot_stride;
+                const SPtr sc = stage + (2 * P.rp + ty) * P.K * P.slot_stride;
 #pragma unroll
                 for (int p = 0; p < BW / 2; ++p) {
                     if ((j0 >> 1) + p < P.cw2) {
