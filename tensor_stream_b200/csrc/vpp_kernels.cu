@@ -158,11 +158,16 @@ __device__ __forceinline__ int bicubic_dot(const double c0, const double c1, con
     return b;
 }
 
-// The same row sum, evaluated in float32 first.  |s32 - s_real| < 2e-4 (weights rounded to f32:
-// 4 * 2^-25 * 2 * 255; four f32 roundings at magnitude < 1024), the FP64 chain is within 1e-12 of
-// s_real, so whenever frac(s32 + .5) is farther than 2^-9 from an integer, floor(s32 + .5) IS
-// round(s64).  Otherwise -- or never, when the weights are multiples of 2^-12 and the f32 sum is
-// exact, ties included -- fall back to the reference's FP64 chain.  Bit-exact by construction.
+// The same row sum, evaluated in float32 first.  With t32 = fl(s32 + .5):
+//   |t32 - (s_real + .5)| <= 2^-24 * 255 * sum|c_k|   (weights rounded to f32, sum|c_k| <= 1.3)   2.0e-5
+//                          + 2^-17                      (fmul, |c1*d1| < 256)                        0.8e-5
+//                          + 4 * 2^-16                  (three fma and the +.5, magnitudes < 512)    6.1e-5
+//                         <  8.9e-5 < 2^-13,
+// and the FP64 chain is within 1e-12 of s_real.  So whenever frac(t32) is farther than 2^-12 from an
+// integer, floor(t32) IS round(s64).  Otherwise -- or never, when the weights are multiples of 2^-12
+// and the f32 sum is exact, ties included -- fall back to the reference's FP64 chain.  Bit-exact by
+// construction; the window only sets how often the slow path runs (a tie-prone 1.5x resize lands in
+// it for 1/256 + 2^-11 of the dots instead of 1/256 + 2^-8 with the 2^-9 window of round 1).
 __device__ __forceinline__ int bicubic_dot_fast(const float *cf, const double *cd, int exact, uint32_t d0, uint32_t d1,
                                                 uint32_t d2, uint32_t d3) {
     float s = __fmul_rn(cf[1], u2f(d1));
@@ -173,7 +178,7 @@ __device__ __forceinline__ int bicubic_dot_fast(const float *cf, const double *c
     const uint32_t r = f2u8_sat(t);  // floor(t) for 0 <= t < 256, saturated outside: clamp(round-half-up(s))
     if (!exact) {
         const float frac = __fsub_rn(t, u2f(r));  // in [0,1) wherever the rounding can matter
-        const float eps = 0.001953125f;           // 2^-9
+        const float eps = 0.000244140625f;        // 2^-12
         if (t >= 0.0f && (frac < eps || frac > 1.0f - eps))
             return bicubic_dot(cd[0], cd[1], cd[2], cd[3], (int)d0, (int)d1, (int)d2, (int)d3);
     }
