@@ -487,8 +487,25 @@ def run_reference(args):
     ref.close()
 
 
+def bind_process_to_gpu_node():
+    """Optional (TSVPP_BENCH_BIND=1): run the whole arm -- driver calls included -- on the CPUs of the
+    GPU's NUMA node, as a numactl-launched deployment would.  Off by default: the CPU baselines want
+    every core, and the per-buffer binding in the e2e sections is what the zero-copy path needs."""
+    if os.environ.get("TSVPP_BENCH_BIND") != "1":
+        return None
+    from tensor_stream_b200 import numa
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    node = numa.gpu_numa_node(local)
+    cpus = (numa.node_cpus(node) & os.sched_getaffinity(0)) if node is not None else set()
+    if cpus:
+        os.sched_setaffinity(0, cpus)
+        return node
+    return None
+
+
 def main():
     args = parse()
+    bind_process_to_gpu_node()
     if args.impl == "reference":
         run_reference(args)
     else:
