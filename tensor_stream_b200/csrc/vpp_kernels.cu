@@ -929,12 +929,17 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
 // ---------------------------------------------------------------------------------------
 // Direct kernel: colour conversion / layout at the source size (the reference's default read():
 // no resize, optional crop).  Nothing is re-used between output blocks, so there is nothing to
-// stage: a warp takes 128 consecutive 2x4 blocks of a frame (row-major over blocks), every lane
-// owns blocks lane, lane+32, lane+64, lane+96 -- its three 32-bit loads per block (two luma rows,
-// one chroma row) and its stores are then contiguous across the warp.  All twelve loads of a lane
-// are issued before the first conversion.  Same arithmetic as the fused kernel (emit_block).
+// stage: a warp takes 32*kDirectSub consecutive 2x4 blocks of a frame (row-major over blocks), every
+// lane owns blocks lane, lane+32, ... -- its three 32-bit loads per block (two luma rows, one chroma
+// row) and its stores are then contiguous across the warp.  All loads of a lane are issued before
+// the first conversion.  Same arithmetic as the fused kernel (emit_block).
 // ---------------------------------------------------------------------------------------
-constexpr int kDirectSub = 4;  // blocks per lane
+// blocks per lane: 2 (32 registers, 8 CTAs = 64 warps per SM) measured 530 k fps on 1080p RGB24, 4 (40
+// registers, 48 warps) 486 k, 8 (48 registers, 40 warps) 469 k -- same box, profiles/r1b_direct_blocks_per_lane.md
+#ifndef TSVPP_DIRECT_SUB
+#define TSVPP_DIRECT_SUB 2
+#endif
+constexpr int kDirectSub = TSVPP_DIRECT_SUB;
 
 // one warp unit in flight: where it goes and the words it loaded
 struct DirectUnit {
