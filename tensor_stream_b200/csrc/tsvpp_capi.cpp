@@ -689,7 +689,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     // direct path: no resize (rows and columns affine with unit step, nothing clamped), 4-column
     // blocks, 32-bit aligned loads
     {
-        bool direct = rs == RS_NEAREST && bulk && dw % 4 == 0 && dh % 2 == 0 && dw >= 4 && dh >= 2 &&
+        bool direct = rs == RS_NEAREST && bulk && dw % 4 == 0 && dh % 2 == 0 && dw >= 8 && dh >= 2 &&
                       !env_int("TSVPP_NO_DIRECT", 0);
         for (int j = 0; j < dw && direct; ++j) {
             if (tap_l[(size_t)j * 4] != tap_l[0] + j) direct = false;
@@ -701,6 +701,23 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             for (int ci = 0; ci < dh / 2 && direct; ++ci)
                 if (rowsrc_c[(size_t)ci * K] != rowsrc_c[0] + ci) direct = false;
         if (direct && ((tap_l[0] & 3) || (need_uv && (tap_c[0] & 3)))) direct = false;
+        // block index -> (row pair, column group) without an integer division in the kernel: with
+        // L = ceil(log2(d)), M = floor(2^(31+L) / d) + 1, n / d == (n * M) >> (31 + L) for all n < 2^31
+        D.d_div_mul = 0;
+        D.d_div_shift = 0;
+        if (direct) {
+            const unsigned d = (unsigned)(dw / 4);
+            int L = 0;
+            while ((1u << L) < d) ++L;
+            const unsigned long long M = ((1ull << (31 + L)) / d) + 1;
+            D.d_div_mul = (unsigned)M;
+            D.d_div_shift = L - 1;
+            const unsigned long long last = (unsigned long long)d * (unsigned)(dh / 2) + 4096;  // a unit may overrun the frame
+            for (unsigned long long n = d - 1; n <= last && direct; n += d) {  // every n = k*d - 1 and k*d
+                if (((n * M) >> (31 + L)) != n / d || (((n + 1) * M) >> (31 + L)) != (n + 1) / d) direct = false;
+            }
+            if (M >> 32) direct = false;
+        }
         D.direct = direct ? 1 : 0;
         D.d_row_l0 = direct ? rowsrc_l[0] : 0;
         D.d_row_c0 = (direct && need_uv) ? rowsrc_c[0] : 0;

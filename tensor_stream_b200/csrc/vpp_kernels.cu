@@ -948,18 +948,18 @@ struct DirectUnit {
     uint32_t w0[kDirectSub], w1[kDirectSub], wc[kDirectSub];
 };
 
+// `f`: frame, `uu`: warp unit inside the frame
 template <bool NEED_UV>
-__device__ __forceinline__ void direct_load(const PlanDev &P, const FrameDev *__restrict__ frames, unsigned u,
-                                            unsigned upf, int ngx, int npr, int lane, DirectUnit &d) {
-    const unsigned f = u / upf;
-    const int g0 = (int)(u - f * upf) * (32 * kDirectSub) + lane;
+__device__ __forceinline__ void direct_load(const PlanDev &P, const FrameDev *__restrict__ frames, unsigned f,
+                                            unsigned uu, int ngx, int npr, int lane, DirectUnit &d) {
+    const int g0 = (int)uu * (32 * kDirectSub) + lane;
     const unsigned long long *fd = reinterpret_cast<const unsigned long long *>(frames + f);
     const unsigned char *fy = reinterpret_cast<const unsigned char *>(__ldg(fd));
     const unsigned char *fuv = reinterpret_cast<const unsigned char *>(__ldg(fd + 1));
     d.out = reinterpret_cast<void *>(__ldg(fd + 2));
     fy += (size_t)P.d_row_l0 * P.pitch_y + P.d_x_l0;
     fuv += (size_t)P.d_row_c0 * P.pitch_uv + P.d_x_c0;
-    int pr = (int)((unsigned)g0 / (unsigned)ngx), gx = g0 - pr * ngx;
+    int pr = (int)(__umulhi((unsigned)g0, P.d_div_mul) >> P.d_div_shift), gx = g0 - pr * ngx;  // g0 / ngx (plan)
     d.pr0 = pr;
     d.gx0 = gx;
 #pragma unroll
@@ -1012,20 +1012,20 @@ __device__ __forceinline__ void direct_emit(const PlanDev &P, int ngx, int npr, 
     }
 }
 
-// One unit per warp.  A persistent variant that prefetched the next unit's loads needed 64 instead of
-// 40 registers (4 instead of 6 CTAs per SM) and was 15 % slower (478 k vs 409 k fps, same box): the
-// load latency is better hidden by occupancy here.
+// One unit per warp; blockIdx.y is the frame.  A persistent variant that prefetched the next unit's loads
+// needed 64 instead of 40 registers (4 instead of 6 CTAs per SM) and was 15 % slower (478 k vs 409 k fps,
+// same box): the load latency is better hidden by occupancy here.
 template <int OK>
 __global__ void __launch_bounds__(256) vpp_direct_kernel(const PlanDev P, const FrameDev *__restrict__ frames,
-                                                                 int nframes, int vec_ok) {
+                                                         int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     const int lane = threadIdx.x & 31;
     const int ngx = P.dw >> 2, npr = P.dh >> 1;
-    const unsigned upf = (unsigned)(ngx * npr + 32 * kDirectSub - 1) / (32 * kDirectSub);
-    const unsigned u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (u >= upf * (unsigned)nframes) return;
+    const unsigned upf = (unsigned)(ngx * npr + 32 * kDirectSub - 1) / (32 * kDirectSub);  // warp units per frame
+    const unsigned uu = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (uu >= upf || (int)blockIdx.y >= nframes) return;
     DirectUnit cur;
-    direct_load<NEED_UV>(P, frames, u, upf, ngx, npr, lane, cur);
+    direct_load<NEED_UV>(P, frames, blockIdx.y, uu, ngx, npr, lane, cur);
     direct_emit<OK>(P, ngx, npr, vec_ok, cur);
 }
 
@@ -1049,9 +1049,12 @@ int launch_direct(int ok, const PlanDev &P, const FrameDev *frames_dev, int nfra
     if (!fn) return (int)cudaErrorMissingConfiguration;
     const int ngx = P.dw >> 2, npr = P.dh >> 1;
     const long upf = ((long)ngx * npr + 32 * kDirectSub - 1) / (32 * kDirectSub);
-    const long units = upf * nframes;
-    if (units <= 0 || units >= 0x7fffffffL) return (int)cudaErrorInvalidConfiguration;
-    fn<<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(P, frames_dev, nframes, vec_ok);
+    const long gx = (upf + 7) / 8;
+    if (gx <= 0 || gx > 0x7fffffffL) return (int)cudaErrorInvalidConfiguration;
+    for (int f0 = 0; f0 < nframes; f0 += 65535) {  // gridDim.y limit
+        const int nf = std::min(65535, nframes - f0);
+        fn<<<dim3((unsigned)gx, (unsigned)nf), 256, 0, stream>>>(P, frames_dev + f0, nf, vec_ok);
+    }
     return (int)cudaGetLastError();
 }
 

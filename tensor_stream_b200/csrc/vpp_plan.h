@@ -76,6 +76,8 @@ struct PlanDev {
     int direct;             // 1: the plan may run vpp_direct_kernel
     int d_row_l0, d_row_c0; // source row of output luma row 0 / chroma row 0
     int d_x_l0, d_x_c0;     // source byte of output column 0 in a luma / chroma row (multiples of 4)
+    unsigned d_div_mul;     // n / (dw/4) == __umulhi(n, d_div_mul) >> d_div_shift for every block index n of a frame
+    int d_div_shift;
     // tables (device pointers)
     const int *seg_a0_l;    // [ntiles] byte offset of the staged segment inside a luma row
     const int *seg_len_l;   // [ntiles] bytes (multiple of 16)
