@@ -256,7 +256,6 @@ struct Plan {
 
 struct TsvppContext {
     int device = 0;
-    bool frames_in_host_memory = false;  // set around launches of the zero-copy host path
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;
     std::mutex mu;
@@ -926,8 +925,11 @@ static int upload_descriptors(TsvppContext *ctx, const FrameDev *src, int n, cud
 
 // UYVY / YUV444: (fused crop+resize -> tight NV12 u8, only when needed) + one packing kernel
 // (reference src/ColorConversion.cu:336-352)
+static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                              void *const *out, cudaStream_t stream, bool frames_on_host);
+
 static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
-                              void *const *out, cudaStream_t stream) {
+                              void *const *out, cudaStream_t stream, bool frames_on_host) {
     const int W = frames[0].width, H = frames[0].height;
     const Geometry g = resolve_geometry(W, H, *p);
     const int is_float = p->normalization ? 1 : 0;
@@ -946,7 +948,7 @@ static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n
         TSVPP_CUDA(cudaMemsetAsync(tmp, 0, fbytes * n, stream));
         std::vector<void *> o1(n);
         for (int i = 0; i < n; ++i) o1[i] = tmp + fbytes * i;
-        int rc = tsvpp_convert_batch(ctx, frames, n, &p1, o1.data(), stream);
+        int rc = convert_batch_impl(ctx, frames, n, &p1, o1.data(), stream, frames_on_host);
         if (rc) {
             cudaFreeAsync(tmp, stream);
             return rc;
@@ -985,13 +987,15 @@ static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n
     return rc;
 }
 
-int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
-                        void *stream_) {
+// frames_on_host: the planes are device-mapped pinned host memory (zero-copy host path): keep the
+// row-segment bulk copies of the fused kernel instead of the direct kernel's 32-bit loads
+static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                              void *const *out, cudaStream_t stream, bool frames_on_host) {
     if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
-    cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_uniform(frames, n);
     if (rc) return rc;
-    if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444) return convert_packed_yuv(ctx, frames, n, p, out, stream);
+    if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444)
+        return convert_packed_yuv(ctx, frames, n, p, out, stream, frames_on_host);
     const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
     Plan *pl = nullptr;
     rc = get_plan(ctx, frames[0], *p, bulk, &pl);
@@ -1006,12 +1010,16 @@ int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, cons
     rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
     if (rc) return rc;
     (void)cudaGetLastError();  // drop stale non-sticky errors of unrelated earlier calls
-    rc = launch_plan(pl, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n), grid_for(ctx, pl, n), stream,
-                     !ctx->frames_in_host_memory);
+    rc = launch_plan(pl, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n), grid_for(ctx, pl, n), stream, !frames_on_host);
     TSVPP_CUDA(cudaEventRecord(ctx->ring_ev[slot], stream));
     ctx->launches.fetch_add(1);
     if (rc) return note_error(rc, "launch_fused", __LINE__);
     return rc;
+}
+
+int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
+                        void *stream) {
+    return convert_batch_impl(ctx, frames, n, p, out, (cudaStream_t)stream, false);
 }
 
 int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
@@ -1152,9 +1160,7 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
             f[i].y = zy[i];
             f[i].uv = zuv[i];
         }
-        ctx->frames_in_host_memory = true;  // in-place reads over PCIe: keep the bulk-copy row fetches
-        rc = tsvpp_convert_batch(ctx, f.data(), n, p, zout.data(), ctx->hstream[0]);
-        ctx->frames_in_host_memory = false;
+        rc = convert_batch_impl(ctx, f.data(), n, p, zout.data(), ctx->hstream[0], true);
         if (rc) return rc;
         TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
         return TSVPP_OK;
@@ -1180,9 +1186,7 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
             }
             douts[k] = zc_out ? zout[base + k] : (void *)(ctx->stage_out[which] + out_frame * k);
         }
-        ctx->frames_in_host_memory = zero_copy;
-        rc = tsvpp_convert_batch(ctx, dframes.data(), m, p, douts.data(), st);
-        ctx->frames_in_host_memory = false;
+        rc = convert_batch_impl(ctx, dframes.data(), m, p, douts.data(), st, zero_copy);
         if (rc) return rc;
         if (!zc_out)
             for (int k = 0; k < m; ++k)
