@@ -1,11 +1,12 @@
 """Host-memory placement for the zero-copy host path.
 
 `tsvpp_convert_batch_host` lets the kernel read pinned host frames in place over PCIe.  Those reads
-are latency-bound SM-issued requests: from the GPU's own NUMA node they run at PCIe speed (29.7 k
-1080p frames/s on a B200), from the other socket at a quarter of that (6.8 k, measured on the same
-box type) -- whole-frame cudaMemcpy (copy engines) hardly notices the difference.  Pinned buffers land
-on the node of the thread that allocates them, so allocate them with the thread bound to the GPU's
-node:
+are SM-issued and latency-bound: from most pinned allocations they run at PCIe speed (29-30 k 1080p
+frames/s on a B200), from some at a quarter of that (7 k) -- whole-frame cudaMemcpy (copy engines)
+hardly notices.  The slow case was first blamed on buffers living on the other socket, but it has
+since been seen with buffers bound to the GPU's own node too, so treat placement as something to
+probe, not to assume (bench.py does: GPU node first, then the default placement, then the other
+node, keeping the fastest).  Pinned buffers land on the node of the thread that allocates them:
 
     with numa.bound_to_gpu(0):
         frames = [torch.empty(...).pin_memory() for _ in range(n)]
@@ -59,6 +60,35 @@ def node_cpus(node, sysfs="/sys"):
         return _parse_cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read())
     except OSError:
         return set()
+
+
+def all_nodes(sysfs="/sys"):
+    """NUMA nodes that have CPUs, ascending."""
+    out = []
+    try:
+        names = os.listdir(os.path.join(sysfs, "devices/system/node"))
+    except OSError:
+        return out
+    for name in names:
+        if name.startswith("node") and name[4:].isdigit() and node_cpus(int(name[4:]), sysfs):
+            out.append(int(name[4:]))
+    return sorted(out)
+
+
+@contextlib.contextmanager
+def bound_to_node(node, sysfs="/sys"):
+    """Run the body with the calling thread restricted to the CPUs of NUMA node `node` (no-op when the
+    node has no CPU this process may use).  Yields the node or None."""
+    old = os.sched_getaffinity(0)
+    cpus = (node_cpus(node, sysfs) & old) if node is not None else set()
+    if not cpus:
+        yield None
+        return
+    os.sched_setaffinity(0, cpus)
+    try:
+        yield node
+    finally:
+        os.sched_setaffinity(0, old)
 
 
 @contextlib.contextmanager
