@@ -20,7 +20,10 @@
 //                   positions equal the reference's nvcc -fmad=true contraction), rounded
 //                   through uint8 exactly where the reference stores its NV12 intermediate,
 //                   then converted (BT.601), normalised and stored with vector stores.
-//                   No block-wide barrier anywhere in the steady state.
+//                   No block-wide barrier anywhere in the steady state.  Taps are ld.shared from
+//                   addresses derived from one laundered base register (SPtr below).
+// No-resize conversions on device-resident frames skip the staging altogether (vpp_direct_kernel,
+// further down): nothing is reused between output blocks there, so coalesced loads + occupancy win.
 // uint8 -> float uses cvt.rn.f32.u32 on 32-bit registers (SASS I2FP) and float -> uint8 one
 // saturating cvt.rzi.u8.f32 (SASS F2IP: truncation and the [0,255] clamp in one instruction)
 // instead of the byte-typed I2F/F2I forms the compiler picks for (float)uchar / (int)float

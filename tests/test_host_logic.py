@@ -233,3 +233,41 @@ def test_numa_binding_uses_the_gpu_node_cpus(tmp_path, monkeypatch):
     with numa.bound_to_gpu(0, str(sysfs)) as node:
         assert node is None
         assert sorted(os.sched_getaffinity(0)) == mine
+
+
+def test_numa_node_listing_and_binding(tmp_path):
+    import os
+    from tensor_stream_b200 import numa
+    mine = sorted(os.sched_getaffinity(0))
+    sysfs = tmp_path
+    for node, cpus in ((0, mine[:1]), (1, mine[-1:]), (2, [])):
+        (sysfs / ("devices/system/node/node%d" % node)).mkdir(parents=True)
+        (sysfs / ("devices/system/node/node%d/cpulist" % node)).write_text(",".join(str(c) for c in cpus) + "\n")
+    (sysfs / "devices/system/node/possible").write_text("0-2\n")  # non-node entries are ignored
+    assert numa.all_nodes(str(sysfs)) == [0, 1]                     # node2 has no CPUs
+    with numa.bound_to_node(1, str(sysfs)) as node:
+        assert node == 1 and os.sched_getaffinity(0) == {mine[-1]}
+    with numa.bound_to_node(2, str(sysfs)) as node:                 # nothing to bind to
+        assert node is None and sorted(os.sched_getaffinity(0)) == mine
+    with numa.bound_to_node(None, str(sysfs)) as node:
+        assert node is None
+    assert sorted(os.sched_getaffinity(0)) == mine
+
+
+def test_block_index_division_by_multiply_shift():
+    """The direct kernel decodes a block index n into (row pair, column group) with
+    __umulhi(n, M) >> (L - 1), M = floor(2^(31+L) / d) + 1, L = ceil(log2 d)  (tsvpp_capi.cpp builds M and
+    re-checks it per plan).  Exact for every n < 2^31: e = M*d - 2^(31+L) is in (0, d], so the quotient
+    error n*e / (d * 2^(31+L)) stays below 1/d."""
+    import random
+    rng = random.Random(7)
+    ds = list(range(2, 70)) + [120, 255, 256, 257, 480, 960, 1920, 2048, 4095, 4096, 16384, 65535, 65536, 1 << 20]
+    for d in ds:
+        L = (d - 1).bit_length()
+        M = ((1 << (31 + L)) // d) + 1
+        assert M < (1 << 32)
+        ns = [0, 1, d - 1, d, d + 1, (1 << 31) - 1, ((1 << 31) - 1) // d * d, ((1 << 31) - 1) // d * d - 1]
+        ns += [rng.randrange(1 << 31) for _ in range(200)] + [k * d - 1 for k in range(1, 200)] + [k * d for k in range(1, 200)]
+        for n in ns:
+            if 0 <= n < (1 << 31):
+                assert ((n * M) >> 32) >> (L - 1) == n // d, (d, n)
