@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
             cmd.insert(2, "cu")
         subprocess.check_call(cmd)
         objs.append(o)
-    subprocess.check_call(["nvcc", "-shared", "-o", LIB] + objs + ["-lcuda"])
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcuda"])
     for o in objs:
         os.remove(o)
     return LIB
