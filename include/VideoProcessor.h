@@ -57,6 +57,21 @@ struct FrameParameters {
 float channelsByFourCC(FourCC fourCC);
 float channelsByFourCC(std::string fourCC);
 
+// The reference's stage-level entry points (reference include/VideoProcessor.h:109-115; bodies in
+// src/ColorConversion.cu:280-382, src/Resize.cu:408-473, src/Crop.cu:23-48).  Convert() does NOT go through
+// them here -- it runs crop + resize + colour as one kernel -- but code written against the individual
+// stages keeps working: each function is the fused path restricted to that stage, with the reference's
+// buffer contract (fresh cudaMalloc'd, tight, cudaFree-able buffers in dst->data[0], dst->data[1] or
+// dst->opaque; resizeKernel frees the crop intermediates when `crop` is set; dst->width/height are left to the
+// caller, as in the reference).  A cropHost -> resizeKernel -> colorConversionKernel chain yields the bytes
+// Convert() yields.  maxThreadsPerBlock is accepted and ignored.  colorConversionKernel<float> needs
+// color.normalization (or HSV) and <unsigned char> needs it off -- the pairing Convert() uses
+// (src/VideoProcessor.cpp:139-142); the other two pairings return VREADER_UNSUPPORTED.
+template <class T>
+int colorConversionKernel(AVFrame *src, AVFrame *dst, ColorOptions color, int maxThreadsPerBlock, cudaStream_t *stream);
+int resizeKernel(AVFrame *src, AVFrame *dst, bool crop, ResizeOptions resize, int maxThreadsPerBlock, cudaStream_t *stream);
+int cropHost(AVFrame *src, AVFrame *dst, CropOptions crop, int maxThreadsPerBlock, cudaStream_t *stream);
+
 class VideoProcessor {
 public:
     int Init(std::shared_ptr<Logger> logger, uint8_t maxConsumers = 5, bool _enableDumps = false);

@@ -12,6 +12,8 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "tsvpp.h"
 
@@ -62,6 +64,155 @@ void dump_size(const FrameParameters &o, int &w, int &h) {
     }
 }
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Stage-level entry points (reference include/VideoProcessor.h:109-115)
+// ---------------------------------------------------------------------------------------------
+namespace {
+// one library context per device for callers that have no VideoProcessor object; lives as long as the process
+TsvppContext *stage_context() {
+    static std::mutex mu;
+    static std::map<int, TsvppContext *> by_device;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = by_device.find(dev);
+    if (it != by_device.end()) return it->second;
+    TsvppContext *c = nullptr;
+    if (tsvpp_create(dev, &c) != TSVPP_OK) return nullptr;
+    by_device[dev] = c;
+    return c;
+}
+
+TsvppFrame frame_of(const AVFrame *a) {
+    TsvppFrame f;
+    f.y = a->data[0];
+    f.uv = a->data[1];
+    f.pitch_y = a->linesize[0];  // 0 => width, resolved by the library like the reference (src/Resize.cu:420-421)
+    f.pitch_uv = a->linesize[1];
+    f.width = a->width;
+    f.height = a->height;
+    return f;
+}
+
+// crop and/or resize to a tight NV12 image in two separately cudaFree-able buffers
+int nv12_stage(const AVFrame *src, const TsvppParams &p, unsigned char **y_out, unsigned char **uv_out,
+               cudaStream_t stream) {
+    TsvppContext *ctx = stage_context();
+    if (!ctx) return VREADER_ERROR;
+    const TsvppFrame f = frame_of(src);
+    int w = 0, h = 0, es = 1;
+    size_t elems = 0;
+    int rc = tsvpp_output_info(f.width, f.height, &p, &w, &h, &elems, &es);
+    if (rc) return rc;
+    const size_t y_bytes = (size_t)w * h, uv_bytes = (size_t)w * (h / 2);
+    unsigned char *both = nullptr, *uv = nullptr;
+    cudaError_t e = cudaMalloc(&both, elems * (size_t)es);  // Y plane, then the UV plane the fused NV12 output appends
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMalloc(&uv, uv_bytes ? uv_bytes : 1);
+    if (e != cudaSuccess) {
+        cudaFree(both);
+        return (int)e;
+    }
+    void *outs[1] = {both};
+    rc = tsvpp_convert_batch(ctx, &f, 1, &p, outs, stream);
+    if (rc == TSVPP_OK && uv_bytes)
+        rc = (int)cudaMemcpyAsync(uv, both + y_bytes, uv_bytes, cudaMemcpyDeviceToDevice, stream);
+    if (rc) {
+        cudaFree(both);
+        cudaFree(uv);
+        return rc;
+    }
+    *y_out = both;  // the caller's cudaFree(data[0]) releases the whole allocation
+    *uv_out = uv;
+    return VREADER_OK;
+}
+}  // namespace
+
+int cropHost(AVFrame *src, AVFrame *dst, CropOptions crop, int /*maxThreadsPerBlock*/, cudaStream_t *stream) {
+    if (!src || !dst || !stream) return VREADER_ERROR;
+    const int x0 = std::get<0>(crop.leftTopCorner), y0 = std::get<1>(crop.leftTopCorner);
+    const int x1 = std::get<0>(crop.rightBottomCorner), y1 = std::get<1>(crop.rightBottomCorner);
+    const int cw = x1 - x0, ch = y1 - y0;
+    if (cw <= 0 || ch <= 0 || x0 < 0 || y0 < 0 || x1 > src->width || y1 > src->height) return VREADER_ERROR;
+    // the library applies a crop under Convert's rule (0 < cw < W && 0 < ch < H, src/VideoProcessor.cpp:109);
+    // a box that spans a full dimension is only the identity here
+    const bool active = cw < src->width && ch < src->height;
+    if (!active && (x0 != 0 || y0 != 0 || cw != src->width || ch != src->height)) return VREADER_UNSUPPORTED;
+    TsvppParams p;
+    p.crop_x0 = active ? x0 : 0;
+    p.crop_y0 = active ? y0 : 0;
+    p.crop_x1 = active ? x1 : 0;
+    p.crop_y1 = active ? y1 : 0;
+    p.dst_width = p.dst_height = 0;
+    p.resize_type = (int)NEAREST;
+    p.fourcc = (int)NV12;
+    p.planes = (int)MERGED;
+    p.normalization = 0;
+    unsigned char *y = nullptr, *uv = nullptr;
+    const int rc = nv12_stage(src, p, &y, &uv, *stream);
+    if (rc) return rc;
+    dst->data[0] = y;
+    dst->data[1] = uv;
+    return VREADER_OK;
+}
+
+int resizeKernel(AVFrame *src, AVFrame *dst, bool crop, ResizeOptions resize, int /*maxThreadsPerBlock*/,
+                 cudaStream_t *stream) {
+    if (!src || !dst || !stream || resize.width == 0 || resize.height == 0) return VREADER_ERROR;
+    TsvppParams p;
+    p.crop_x0 = p.crop_y0 = p.crop_x1 = p.crop_y1 = 0;
+    p.dst_width = (int)resize.width;
+    p.dst_height = (int)resize.height;
+    p.resize_type = (int)resize.type;
+    p.fourcc = (int)NV12;
+    p.planes = (int)MERGED;
+    p.normalization = 0;
+    unsigned char *y = nullptr, *uv = nullptr;
+    const int rc = nv12_stage(src, p, &y, &uv, *stream);
+    if (rc) return rc;
+    if (crop) {  // the crop intermediates (dst may be src): cudaFree waits for the work queued above
+        cudaFree(dst->data[0]);
+        cudaFree(dst->data[1]);
+    }
+    dst->data[0] = y;
+    dst->data[1] = uv;
+    return VREADER_OK;
+}
+
+template <class T>
+int colorConversionKernel(AVFrame *src, AVFrame *dst, ColorOptions color, int /*maxThreadsPerBlock*/,
+                          cudaStream_t *stream) {
+    if (!src || !dst || !stream) return VREADER_ERROR;
+    TsvppContext *ctx = stage_context();
+    if (!ctx) return VREADER_ERROR;
+    TsvppParams p;
+    p.crop_x0 = p.crop_y0 = p.crop_x1 = p.crop_y1 = 0;
+    p.dst_width = p.dst_height = 0;
+    p.resize_type = (int)NEAREST;
+    p.fourcc = (int)color.dstFourCC;
+    p.planes = (int)color.planesPos;
+    p.normalization = color.normalization ? 1 : 0;
+    const TsvppFrame f = frame_of(src);
+    int w = 0, h = 0, es = 1;
+    size_t elems = 0;
+    int rc = tsvpp_output_info(f.width, f.height, &p, &w, &h, &elems, &es);
+    if (rc) return rc;  // unknown FourCC: cudaErrorMissingConfiguration (src/ColorConversion.cu:376)
+    if ((size_t)es != sizeof(T)) return VREADER_UNSUPPORTED;
+    void *buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, elems * sizeof(T));
+    if (e != cudaSuccess) return (int)e;
+    void *outs[1] = {buf};
+    rc = tsvpp_convert_batch(ctx, &f, 1, &p, outs, *stream);
+    if (rc) {
+        cudaFree(buf);
+        return rc;
+    }
+    dst->opaque = buf;
+    return VREADER_OK;
+}
+template int colorConversionKernel<unsigned char>(AVFrame *, AVFrame *, ColorOptions, int, cudaStream_t *);
+template int colorConversionKernel<float>(AVFrame *, AVFrame *, ColorOptions, int, cudaStream_t *);
 
 int VideoProcessor::Init(std::shared_ptr<Logger> lg, uint8_t maxConsumers, bool _enableDumps) {
     enableDumps = _enableDumps;
