@@ -412,6 +412,8 @@ def run_ours(args):
                      "traffic": ((traffic or {}).get("dram_bytes_per_frame") or 0) * n or None,
                      "traffic_source": (traffic or {}).get("source"),
                      "algorithmic_bytes_per_frame": B_FULL, "frames_per_launch": n,
+                     # BASELINE.json also asks for source luma pixels per second (per GPU, from the launch time)
+                     "src_gpixel_per_s_per_gpu": n * W * H / (avg_launch * 1e-3) / 1e9,
                      "launch_ms_avg": avg_launch, "launch_ms_median": med_launch, "peak_source": peak_src,
                      "note": "achieved = frames_per_launch * B_full / launch time (CUDA events); the kernel fetches only "
                              "the source rows its taps touch, so DRAM traffic < B_full and frac can exceed 1"},
