@@ -82,11 +82,14 @@ Geometry resolve_geometry(int W, int H, const TsvppParams &p) {
 }
 
 // channelsByFourCC -- reference src/VideoProcessor.cpp:4-14
-float channels_of(int fourcc) {
-    if (fourcc == TSVPP_Y800) return 1.f;
-    if (fourcc == TSVPP_UYVY) return 2.f;
-    if (fourcc == TSVPP_NV12) return 1.5f;
-    return 3.f;
+// channels * w * h of the reference's (size_t)(channelsByFourCC * w * h) allocations, in exact integer
+// arithmetic (a float product is only exact below 2^24 elements)
+size_t elems_of(int fourcc, int w, int h) {
+    const size_t px = (size_t)w * (size_t)h;
+    if (fourcc == TSVPP_Y800) return px;
+    if (fourcc == TSVPP_UYVY) return 2 * px;
+    if (fourcc == TSVPP_NV12) return px + px / 2;  // floor(1.5 * w * h)
+    return 3 * px;
 }
 
 int out_kind_of(const TsvppParams &p) {
@@ -753,8 +756,8 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     if (cap_ctas > 0) pl->ctas_per_sm = std::min(pl->ctas_per_sm, cap_ctas);
     pl->out_w = dw;
     pl->out_h = dh;
-    pl->out_elems = (size_t)(channels_of(p.fourcc) * dw * dh);
-    if ((double)channels_of(p.fourcc) * dw * dh >= 4294967296.0) return TSVPP_UNSUPPORTED;  // 32-bit element offsets
+    pl->out_elems = elems_of(p.fourcc, dw, dh);
+    if (pl->out_elems >= 4294967296ull) return TSVPP_UNSUPPORTED;  // 32-bit element offsets
     pl->elem_size = (p.normalization || p.fourcc == TSVPP_HSV) ? 4 : 1;
     pl->vec_ok_geom = (dw % bw == 0) ? 1 : 0;
     // bytes one frame's work items fetch from the source planes (what crosses HBM / PCIe)
@@ -889,7 +892,7 @@ int tsvpp_output_info(int src_width, int src_height, const TsvppParams *p, int *
     const Geometry g = resolve_geometry(src_width, src_height, *p);
     if (out_w) *out_w = g.dw;
     if (out_h) *out_h = g.dh;
-    if (elems) *elems = (size_t)(channels_of(p->fourcc) * g.dw * g.dh);
+    if (elems) *elems = elems_of(p->fourcc, g.dw, g.dh);
     if (elem_size) *elem_size = (p->normalization || p->fourcc == TSVPP_HSV) ? 4 : 1;
     return TSVPP_OK;
 }

@@ -271,3 +271,13 @@ def test_block_index_division_by_multiply_shift():
         for n in ns:
             if 0 <= n < (1 << 31):
                 assert ((n * M) >> 32) >> (L - 1) == n // d, (d, n)
+
+
+def test_output_element_counts_are_exact_for_large_odd_sizes(lib):
+    """channels * w * h is computed in integers: a float product (the reference's (size_t)(channels*w*h)) is
+    exact only below 2^24 elements and would round 3*5001*4001 to a neighbouring multiple of 4."""
+    from tensor_stream_b200 import vpp
+    for fourcc, want in ((vpp.FourCC.RGB24, 3 * 5001 * 4001), (vpp.FourCC.UYVY, 2 * 5001 * 4001),
+                         (vpp.FourCC.NV12, 5001 * 4001 + (5001 * 4001) // 2), (vpp.FourCC.Y800, 5001 * 4001)):
+        w, h, n, es = vpp.output_info(5001, 4001, vpp.FrameParameters(pixel_format=fourcc))
+        assert (w, h, n, es) == (5001, 4001, want, 1)
