@@ -11,10 +11,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <list>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -42,6 +44,45 @@ inline int note_error(int code, const char *what, int line) {
         cudaError_t e_ = (expr);                                      \
         if (e_ != cudaSuccess) return note_error((int)e_, #expr, __LINE__); \
     } while (0)
+
+// Every entry point that allocates, builds a plan or launches runs on the CONTEXT's device and puts the
+// caller's current device back on exit: two contexts on different GPUs may be driven from one thread, and a
+// Python __del__ -> tsvpp_destroy must not change torch's current device behind its back.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define TSVPP_ON_DEVICE(ctx)                                                        \
+    DeviceGuard device_guard_((ctx)->device);                                       \
+    if (device_guard_.err != cudaSuccess) return note_error((int)device_guard_.err, "cudaSetDevice", __LINE__)
+
+// no C++ exception may cross the C ABI (std::bad_alloc / length_error from a plan build would terminate a
+// cgo / JNI / ctypes caller)
+template <class F>
+int abi_guard(F &&f, int line) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return note_error((int)cudaErrorMemoryAllocation, "std::bad_alloc", line);
+    } catch (const std::exception &e) {
+        return note_error(TSVPP_ERROR, e.what(), line);
+    } catch (...) {
+        return note_error(TSVPP_ERROR, "unknown C++ exception", line);
+    }
+}
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int env_int(const char *name, int dflt) {
@@ -79,6 +120,17 @@ Geometry resolve_geometry(int W, int H, const TsvppParams &p) {
         g.dh = p.dst_height;
     }
     return g;
+}
+
+// What the reference never checks and then indexes with: sizes must be positive (a frame has at least one
+// chroma row), the requested output size non-negative and small enough for 32-bit tables.  A crop box that
+// leaves the frame stays accepted: its taps are clamped into the frame (the reference reads out of bounds).
+int validate_geometry(int W, int H, const TsvppParams &p) {
+    if (W <= 0 || H < 2 || W > (1 << 16) || H > (1 << 16)) return TSVPP_ERROR;
+    if (p.dst_width < 0 || p.dst_height < 0 || p.dst_width > (1 << 16) || p.dst_height > (1 << 16)) return TSVPP_ERROR;
+    const Geometry g = resolve_geometry(W, H, p);
+    if (g.sw <= 0 || g.sh <= 0 || g.dw <= 0 || g.dh <= 0) return TSVPP_ERROR;
+    return TSVPP_OK;
 }
 
 // channelsByFourCC -- reference src/VideoProcessor.cpp:4-14
@@ -235,6 +287,7 @@ struct PlanKey {
     int w, h, pitch_y, pitch_uv, bulk;
     TsvppParams p;
     bool operator<(const PlanKey &o) const { return std::memcmp(this, &o, sizeof(PlanKey)) < 0; }
+    bool operator==(const PlanKey &o) const { return std::memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
 
 struct Plan {
@@ -262,7 +315,10 @@ struct TsvppContext {
     int sm_count = 148;
     size_t smem_optin = 227 * 1024;
     std::mutex mu;
-    std::map<PlanKey, std::unique_ptr<Plan>> plans;
+    // plan cache: shared ownership (a launch in flight or a TsvppBatch keeps its plan alive), LRU-bounded
+    std::map<PlanKey, std::shared_ptr<Plan>> plans;
+    std::list<PlanKey> lru;  // most recently used first
+    size_t max_plans = 64;
     std::atomic<unsigned long long> launches{0};
     // descriptor ring for tsvpp_convert_batch (pinned host + device), guarded by events
     static constexpr int kRing = 32;  // concurrent convert calls in flight (the reference allows maxConsumers = 5 by default)
@@ -270,7 +326,11 @@ struct TsvppContext {
     FrameDev *ring_dev[kRing] = {};
     cudaEvent_t ring_ev[kRing] = {};
     int ring_cap[kRing] = {};
+    bool ring_busy[kRing] = {};    // claimed by a call that has not yet recorded its event
+    bool ring_recorded[kRing] = {};
     int ring_next = 0;
+    std::condition_variable ring_cv;
+    std::mutex host_mu;  // tsvpp_convert_batch_host owns hstream / stage_in / stage_out for the whole call
     // host-buffer path
     cudaStream_t hstream[2] = {};
     unsigned char *stage_in[2] = {};
@@ -282,7 +342,7 @@ struct TsvppContext {
 
 struct TsvppBatch {
     TsvppContext *ctx = nullptr;
-    Plan *plan = nullptr;
+    std::shared_ptr<Plan> plan;
     // UYVY / YUV444 batches replay the two-kernel path from a host copy of the descriptors
     bool packed_yuv = false;
     TsvppParams params{};
@@ -298,7 +358,7 @@ namespace {
 
 int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in, const TsvppParams &p, bool bulk,
                std::unique_ptr<Plan> &out) {
-    if (W <= 0 || H <= 0) return TSVPP_ERROR;
+    if (int vrc = validate_geometry(W, H, p)) return vrc;
     std::unique_ptr<Plan> pl(new Plan());
     const Geometry g = resolve_geometry(W, H, p);
     const int ok = out_kind_of(p);
@@ -529,16 +589,19 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
         std::vector<double> wall((size_t)dw + nrows_l);
         for (int j = 0; j < dw; ++j) wall[j] = xs[j].wd;
         for (int i = 0; i < nrows_l; ++i) wall[(size_t)dw + i] = wyd[i];
-        double *dW = nullptr, *dC = nullptr;
+        struct DevBuf {  // freed on every exit path
+            double *p = nullptr;
+            ~DevBuf() {
+                if (p) cudaFree(p);
+            }
+        } dW, dC;
         const int n = (int)wall.size();
-        TSVPP_CUDA(cudaMalloc(&dW, sizeof(double) * n));
-        TSVPP_CUDA(cudaMalloc(&dC, sizeof(double) * 4 * n));
-        TSVPP_CUDA(cudaMemcpy(dW, wall.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
-        launch_bicubic_weights(dW, dC, n, 0);
+        TSVPP_CUDA(cudaMalloc(&dW.p, sizeof(double) * n));
+        TSVPP_CUDA(cudaMalloc(&dC.p, sizeof(double) * 4 * n));
+        TSVPP_CUDA(cudaMemcpy(dW.p, wall.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+        launch_bicubic_weights(dW.p, dC.p, n, 0);
         std::vector<double> call((size_t)4 * n);
-        TSVPP_CUDA(cudaMemcpy(call.data(), dC, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
-        cudaFree(dW);
-        cudaFree(dC);
+        TSVPP_CUDA(cudaMemcpy(call.data(), dC.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
         cxw.assign(call.begin(), call.begin() + (size_t)4 * dw);
         cyw.assign(call.begin() + (size_t)4 * dw, call.end());
     }
@@ -786,7 +849,7 @@ bool frames_bulk_ok(const TsvppFrame *f, int n) {
     return true;
 }
 
-int get_plan(TsvppContext *ctx, const TsvppFrame &f0, const TsvppParams &p, bool bulk, Plan **out) {
+int get_plan(TsvppContext *ctx, const TsvppFrame &f0, const TsvppParams &p, bool bulk, std::shared_ptr<Plan> *out) {
     PlanKey key;
     std::memset(&key, 0, sizeof(key));
     key.w = f0.width;
@@ -795,15 +858,41 @@ int get_plan(TsvppContext *ctx, const TsvppFrame &f0, const TsvppParams &p, bool
     key.pitch_uv = f0.pitch_uv ? f0.pitch_uv : f0.width;
     key.bulk = bulk ? 1 : 0;
     key.p = p;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    auto it = ctx->plans.find(key);
-    if (it == ctx->plans.end()) {
-        std::unique_ptr<Plan> pl;
-        int rc = build_plan(ctx, key.w, key.h, key.pitch_y, key.pitch_uv, p, bulk, pl);
-        if (rc) return rc;
-        it = ctx->plans.emplace(key, std::move(pl)).first;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->plans.find(key);
+        if (it != ctx->plans.end()) {
+            // move to the front of the LRU list (the list is short: max_plans entries)
+            ctx->lru.remove(key);
+            ctx->lru.push_front(key);
+            *out = it->second;
+            return TSVPP_OK;
+        }
     }
-    *out = it->second.get();
+    // Build OUTSIDE the context lock (table upload, for bicubic a small kernel): other consumers keep
+    // converting meanwhile.  Two threads may build the same plan once; the first insert wins.
+    std::unique_ptr<Plan> pl;
+    int rc = build_plan(ctx, key.w, key.h, key.pitch_y, key.pitch_uv, p, bulk, pl);
+    if (rc) return rc;
+    std::shared_ptr<Plan> sp(pl.release());
+    std::vector<std::shared_ptr<Plan>> evicted;  // destroyed after the lock is dropped
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto ins = ctx->plans.emplace(key, sp);
+        if (ins.second) ctx->lru.push_front(key);
+        *out = ins.first->second;
+        while (ctx->plans.size() > ctx->max_plans && !ctx->lru.empty()) {
+            const PlanKey victim = ctx->lru.back();
+            ctx->lru.pop_back();
+            auto v = ctx->plans.find(victim);
+            if (v != ctx->plans.end()) {
+                // ~Plan frees the device tables with cudaFree, which waits for every launch that may still
+                // read them; holders of the shared_ptr (batches, calls in flight) delay it further
+                evicted.push_back(std::move(v->second));
+                ctx->plans.erase(v);
+            }
+        }
+    }
     return TSVPP_OK;
 }
 
@@ -846,49 +935,57 @@ int grid_for(const TsvppContext *ctx, const Plan *pl, int n) {
 // =========================================================================================
 extern "C" {
 
-const char *tsvpp_version(void) { return "tsvpp-b200 0.1 (sm_100a)"; }
+const char *tsvpp_version(void) { return "tsvpp-b200 0.2 (sm_100a)"; }
 
 const char *tsvpp_last_error(void) { return g_last_error; }
 
 int tsvpp_create(int device, TsvppContext **out) {
     if (!out) return TSVPP_ERROR;
-    int ndev = 0;
-    TSVPP_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return (int)cudaErrorInvalidDevice;
-    TSVPP_CUDA(cudaSetDevice(device));
-    std::unique_ptr<TsvppContext> c(new TsvppContext());
-    c->device = device;
-    int v = 0;
-    TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
-    c->sm_count = v;
-    TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    c->smem_optin = (size_t)v;
-    *out = c.release();
-    return TSVPP_OK;
+    return abi_guard([&]() -> int {
+        int ndev = 0;
+        TSVPP_CUDA(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) return (int)cudaErrorInvalidDevice;
+        DeviceGuard g(device);  // the caller's current device is restored on return
+        if (g.err != cudaSuccess) return note_error((int)g.err, "cudaSetDevice", __LINE__);
+        std::unique_ptr<TsvppContext> c(new TsvppContext());
+        c->device = device;
+        int v = 0;
+        TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+        c->sm_count = v;
+        TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        c->smem_optin = (size_t)v;
+        c->max_plans = (size_t)std::max(1, env_int("TSVPP_MAX_PLANS", 64));
+        *out = c.release();
+        return TSVPP_OK;
+    }, __LINE__);
 }
 
 void tsvpp_destroy(TsvppContext *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
-    for (int i = 0; i < TsvppContext::kRing; ++i) {
-        if (ctx->ring_host[i]) cudaFreeHost(ctx->ring_host[i]);
-        if (ctx->ring_dev[i]) cudaFree(ctx->ring_dev[i]);
-        if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+    {
+        DeviceGuard g(ctx->device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < TsvppContext::kRing; ++i) {
+            if (ctx->ring_host[i]) cudaFreeHost(ctx->ring_host[i]);
+            if (ctx->ring_dev[i]) cudaFree(ctx->ring_dev[i]);
+            if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+            if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+            if (ctx->hstream[i]) cudaStreamDestroy(ctx->hstream[i]);
+            if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
+        }
+        ctx->plans.clear();
+        ctx->lru.clear();
     }
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
-        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
-        if (ctx->hstream[i]) cudaStreamDestroy(ctx->hstream[i]);
-        if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
-    }
-    ctx->plans.clear();
     delete ctx;
 }
 
 int tsvpp_output_info(int src_width, int src_height, const TsvppParams *p, int *out_w, int *out_h, size_t *elems,
                       int *elem_size) {
     if (!p) return TSVPP_ERROR;
+    if (int rc = validate_geometry(src_width, src_height, *p)) return note_error(rc, "invalid frame size / parameters", __LINE__);
     const Geometry g = resolve_geometry(src_width, src_height, *p);
     if (out_w) *out_w = g.dw;
     if (out_h) *out_h = g.dh;
@@ -897,31 +994,78 @@ int tsvpp_output_info(int src_width, int src_height, const TsvppParams *p, int *
     return TSVPP_OK;
 }
 
-// Descriptor upload through a small ring of pinned buffers: stream-ordered, no host sync unless
-// all ring slots are still in flight.
-static int upload_descriptors(TsvppContext *ctx, const FrameDev *src, int n, cudaStream_t stream, int *slot_out) {
-    int slot;
+// Descriptor upload through a small ring of pinned buffers: stream-ordered, no host sync unless every ring
+// slot is still in flight.  A slot belongs to exactly one call from claim to release: it is claimed under the
+// lock (busy), its previous user's event is awaited OUTSIDE the lock, and it is released (with its new event
+// recorded) by release_slot() -- so a later call can neither overwrite the pinned descriptors while the H2D
+// copy is in flight nor wait on an event that was never recorded.
+static int claim_slot(TsvppContext *ctx, int n, int *slot_out) {
+    int slot = -1;
     {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        slot = ctx->ring_next;
-        ctx->ring_next = (ctx->ring_next + 1) % TsvppContext::kRing;
-        if (ctx->ring_ev[slot]) TSVPP_CUDA(cudaEventSynchronize(ctx->ring_ev[slot]));
-        else TSVPP_CUDA(cudaEventCreateWithFlags(&ctx->ring_ev[slot], cudaEventDisableTiming));
-        if (ctx->ring_cap[slot] < n) {
-            if (ctx->ring_host[slot]) cudaFreeHost(ctx->ring_host[slot]);
-            if (ctx->ring_dev[slot]) cudaFree(ctx->ring_dev[slot]);
-            ctx->ring_host[slot] = nullptr;
-            ctx->ring_dev[slot] = nullptr;
-            ctx->ring_cap[slot] = 0;
-            const int cap = std::max(n, 64);
-            TSVPP_CUDA(cudaMallocHost(&ctx->ring_host[slot], sizeof(FrameDev) * cap));
-            TSVPP_CUDA(cudaMalloc(&ctx->ring_dev[slot], sizeof(FrameDev) * cap));
-            ctx->ring_cap[slot] = cap;
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        for (;;) {
+            for (int k = 0; k < TsvppContext::kRing; ++k) {
+                const int c = (ctx->ring_next + k) % TsvppContext::kRing;
+                if (!ctx->ring_busy[c]) {
+                    slot = c;
+                    break;
+                }
+            }
+            if (slot >= 0) break;
+            ctx->ring_cv.wait(lk);  // kRing calls are between claim and release: wait for one of them
         }
+        ctx->ring_busy[slot] = true;
+        ctx->ring_next = (slot + 1) % TsvppContext::kRing;
     }
+    auto fail = [&](int rc) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->ring_busy[slot] = false;
+        ctx->ring_cv.notify_one();
+        return rc;
+    };
+    if (!ctx->ring_ev[slot]) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->ring_ev[slot], cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail(note_error((int)e, "cudaEventCreateWithFlags", __LINE__));
+    } else if (ctx->ring_recorded[slot]) {
+        cudaError_t e = cudaEventSynchronize(ctx->ring_ev[slot]);  // previous user's launch has consumed the descriptors
+        if (e != cudaSuccess) return fail(note_error((int)e, "cudaEventSynchronize", __LINE__));
+    }
+    if (ctx->ring_cap[slot] < n) {
+        if (ctx->ring_host[slot]) cudaFreeHost(ctx->ring_host[slot]);
+        if (ctx->ring_dev[slot]) cudaFree(ctx->ring_dev[slot]);
+        ctx->ring_host[slot] = nullptr;
+        ctx->ring_dev[slot] = nullptr;
+        ctx->ring_cap[slot] = 0;
+        const int cap = std::max(n, 64);
+        cudaError_t e = cudaMallocHost(&ctx->ring_host[slot], sizeof(FrameDev) * cap);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->ring_dev[slot], sizeof(FrameDev) * cap);
+        if (e != cudaSuccess) return fail(note_error((int)e, "descriptor ring allocation", __LINE__));
+        ctx->ring_cap[slot] = cap;
+    }
+    *slot_out = slot;
+    return TSVPP_OK;
+}
+
+// records the slot's event on `stream` (after the launch that reads the descriptors) and frees the slot
+static void release_slot(TsvppContext *ctx, int slot, cudaStream_t stream) {
+    const bool rec = cudaEventRecord(ctx->ring_ev[slot], stream) == cudaSuccess;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->ring_recorded[slot] = rec;
+    ctx->ring_busy[slot] = false;
+    ctx->ring_cv.notify_one();
+}
+
+static int upload_descriptors(TsvppContext *ctx, const FrameDev *src, int n, cudaStream_t stream, int *slot_out) {
+    int slot = -1;
+    int rc = claim_slot(ctx, n, &slot);
+    if (rc) return rc;
     std::memcpy(ctx->ring_host[slot], src, sizeof(FrameDev) * n);
-    TSVPP_CUDA(cudaMemcpyAsync(ctx->ring_dev[slot], ctx->ring_host[slot], sizeof(FrameDev) * n, cudaMemcpyHostToDevice,
-                               stream));
+    cudaError_t e = cudaMemcpyAsync(ctx->ring_dev[slot], ctx->ring_host[slot], sizeof(FrameDev) * n,
+                                    cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+        release_slot(ctx, slot, stream);
+        return note_error((int)e, "cudaMemcpyAsync(descriptors)", __LINE__);
+    }
     *slot_out = slot;
     return TSVPP_OK;
 }
@@ -934,6 +1078,7 @@ static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n
 static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
                               void *const *out, cudaStream_t stream, bool frames_on_host) {
     const int W = frames[0].width, H = frames[0].height;
+    if (int vrc = validate_geometry(W, H, *p)) return note_error(vrc, "invalid frame size / parameters", __LINE__);
     const Geometry g = resolve_geometry(W, H, *p);
     const int is_float = p->normalization ? 1 : 0;
     std::vector<FrameDev> h(n);
@@ -982,7 +1127,7 @@ static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n
         (void)cudaGetLastError();
         rc = launch_packed_yuv(p->fourcc == TSVPP_YUV444, is_float, ctx->ring_dev[slot], n, w, hgt, pitch, y_bytes,
                                uv_bytes, is_float, stream);
-        cudaEventRecord(ctx->ring_ev[slot], stream);
+        release_slot(ctx, slot, stream);
         ctx->launches.fetch_add(1);
         if (rc) note_error(rc, "launch_packed_yuv", __LINE__);
     }
@@ -1000,7 +1145,7 @@ static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n
     if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444)
         return convert_packed_yuv(ctx, frames, n, p, out, stream, frames_on_host);
     const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
-    Plan *pl = nullptr;
+    std::shared_ptr<Plan> pl;
     rc = get_plan(ctx, frames[0], *p, bulk, &pl);
     if (rc) return rc;
     std::vector<FrameDev> h(n);
@@ -1013,8 +1158,9 @@ static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n
     rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
     if (rc) return rc;
     (void)cudaGetLastError();  // drop stale non-sticky errors of unrelated earlier calls
-    rc = launch_plan(pl, ctx->ring_dev[slot], n, vec_ok_for(pl, out, n), grid_for(ctx, pl, n), stream, !frames_on_host);
-    TSVPP_CUDA(cudaEventRecord(ctx->ring_ev[slot], stream));
+    rc = launch_plan(pl.get(), ctx->ring_dev[slot], n, vec_ok_for(pl.get(), out, n), grid_for(ctx, pl.get(), n), stream,
+                     !frames_on_host);
+    release_slot(ctx, slot, stream);
     ctx->launches.fetch_add(1);
     if (rc) return note_error(rc, "launch_fused", __LINE__);
     return rc;
@@ -1022,52 +1168,65 @@ static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n
 
 int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
                         void *stream) {
-    return convert_batch_impl(ctx, frames, n, p, out, (cudaStream_t)stream, false);
+    if (!ctx) return TSVPP_ERROR;
+    return abi_guard([&]() -> int {
+        TSVPP_ON_DEVICE(ctx);
+        return convert_batch_impl(ctx, frames, n, p, out, (cudaStream_t)stream, false);
+    }, __LINE__);
 }
 
 int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
                        TsvppBatch **batch) {
     if (!ctx || !frames || !p || !out || !batch || n <= 0) return TSVPP_ERROR;
-    int rc = check_uniform(frames, n);
-    if (rc) return rc;
-    if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444) {
+    return abi_guard([&]() -> int {
+        TSVPP_ON_DEVICE(ctx);
+        int rc = check_uniform(frames, n);
+        if (rc) return rc;
+        if (p->fourcc == TSVPP_UYVY || p->fourcc == TSVPP_YUV444) {
+            if (int vrc = validate_geometry(frames[0].width, frames[0].height, *p)) return vrc;
+            std::unique_ptr<TsvppBatch> b(new TsvppBatch());
+            b->ctx = ctx;
+            b->packed_yuv = true;
+            b->params = *p;
+            b->n = n;
+            b->frames.assign(frames, frames + n);
+            b->outs.assign(out, out + n);
+            *batch = b.release();
+            return TSVPP_OK;
+        }
+        const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
+        std::shared_ptr<Plan> pl;
+        rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+        if (rc) return rc;
         std::unique_ptr<TsvppBatch> b(new TsvppBatch());
         b->ctx = ctx;
-        b->packed_yuv = true;
-        b->params = *p;
+        b->plan = pl;
         b->n = n;
-        b->frames.assign(frames, frames + n);
-        b->outs.assign(out, out + n);
+        b->vec_ok = vec_ok_for(pl.get(), out, n);
+        b->grid = grid_for(ctx, pl.get(), n);
+        std::vector<FrameDev> h(n);
+        for (int i = 0; i < n; ++i) {
+            h[i].y = frames[i].y;
+            h[i].uv = frames[i].uv;
+            h[i].out = out[i];
+        }
+        TSVPP_CUDA(cudaMalloc(&b->frames_dev, sizeof(FrameDev) * n));
+        cudaError_t e = cudaMemcpy(b->frames_dev, h.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(b->frames_dev);
+            return note_error((int)e, "cudaMemcpy(batch descriptors)", __LINE__);
+        }
         *batch = b.release();
         return TSVPP_OK;
-    }
-    const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
-    Plan *pl = nullptr;
-    rc = get_plan(ctx, frames[0], *p, bulk, &pl);
-    if (rc) return rc;
-    std::unique_ptr<TsvppBatch> b(new TsvppBatch());
-    b->ctx = ctx;
-    b->plan = pl;
-    b->n = n;
-    b->vec_ok = vec_ok_for(pl, out, n);
-    b->grid = grid_for(ctx, pl, n);
-    std::vector<FrameDev> h(n);
-    for (int i = 0; i < n; ++i) {
-        h[i].y = frames[i].y;
-        h[i].uv = frames[i].uv;
-        h[i].out = out[i];
-    }
-    TSVPP_CUDA(cudaMalloc(&b->frames_dev, sizeof(FrameDev) * n));
-    TSVPP_CUDA(cudaMemcpy(b->frames_dev, h.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice));
-    *batch = b.release();
-    return TSVPP_OK;
+    }, __LINE__);
 }
 
 int tsvpp_batch_run(TsvppBatch *b, void *stream) {
     if (!b) return TSVPP_ERROR;
     if (b->packed_yuv)
         return tsvpp_convert_batch(b->ctx, b->frames.data(), b->n, &b->params, b->outs.data(), stream);
-    const Plan *pl = b->plan;
+    TSVPP_ON_DEVICE(b->ctx);
+    const Plan *pl = b->plan.get();
     (void)cudaGetLastError();
     int rc = launch_plan(pl, b->frames_dev, b->n, b->vec_ok, b->grid, (cudaStream_t)stream, true);
     b->ctx->launches.fetch_add(1);
@@ -1077,40 +1236,31 @@ int tsvpp_batch_run(TsvppBatch *b, void *stream) {
 
 void tsvpp_batch_destroy(TsvppBatch *b) {
     if (!b) return;
-    if (b->frames_dev) cudaFree(b->frames_dev);
+    {
+        DeviceGuard g(b->ctx->device);
+        if (b->frames_dev) cudaFree(b->frames_dev);
+        b->plan.reset();
+    }
     delete b;
 }
 
-int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
-                             void *const *out) {
-    if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
+static int convert_batch_host_impl(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                                   void *const *out) {
     int rc = check_uniform(frames, n);
     if (rc) return rc;
-    TSVPP_CUDA(cudaSetDevice(ctx->device));
     const int W = frames[0].width, H = frames[0].height;
     const int py = frames[0].pitch_y ? frames[0].pitch_y : W, puv = frames[0].pitch_uv ? frames[0].pitch_uv : W;
     size_t elems = 0;
     int es = 1, ow = 0, oh = 0;
-    tsvpp_output_info(W, H, p, &ow, &oh, &elems, &es);
+    rc = tsvpp_output_info(W, H, p, &ow, &oh, &elems, &es);
+    if (rc) return rc;
     const size_t in_y = (size_t)py * H, in_uv = (size_t)puv * (H / 2);
     const size_t in_y_pad = (in_y + 255) / 256 * 256, in_uv_pad = (in_uv + 255) / 256 * 256;
     const size_t in_frame = in_y_pad + in_uv_pad;
     const size_t out_frame = (elems * es + 255) / 256 * 256;
-    // chunks of frames ping-pong over two streams so that H2D, kernel and D2H overlap
-    const int chunk = std::max(1, std::min(n, env_int("TSVPP_HOST_CHUNK", 16)));
     for (int s = 0; s < 2; ++s) {
         if (!ctx->hstream[s]) TSVPP_CUDA(cudaStreamCreateWithFlags(&ctx->hstream[s], cudaStreamNonBlocking));
         if (!ctx->hev[s]) TSVPP_CUDA(cudaEventCreateWithFlags(&ctx->hev[s], cudaEventDisableTiming));
-        if (ctx->stage_in_cap[s] < in_frame * chunk) {
-            if (ctx->stage_in[s]) cudaFree(ctx->stage_in[s]);
-            TSVPP_CUDA(cudaMalloc(&ctx->stage_in[s], in_frame * chunk));
-            ctx->stage_in_cap[s] = in_frame * chunk;
-        }
-        if (ctx->stage_out_cap[s] < out_frame * chunk) {
-            if (ctx->stage_out[s]) cudaFree(ctx->stage_out[s]);
-            TSVPP_CUDA(cudaMalloc(&ctx->stage_out[s], out_frame * chunk));
-            ctx->stage_out_cap[s] = out_frame * chunk;
-        }
     }
     // Zero-copy input: when every input plane lives in pinned (page-locked, device-mapped) host
     // memory the fused kernel reads it in place over PCIe -- its bulk copies fetch only the source
@@ -1156,17 +1306,46 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
     }
     ctx->last_host_zero_copy = (zero_copy ? 1 : 0) | (zc_out ? 2 : 0);
     if (zero_copy && zc_out) {
-        // nothing to stage on either side: one launch over the whole batch
+        // Nothing to stage on either side.  The batch is split over the two internal streams so that the
+        // (latency-bound) PCIe reads of one half overlap the posted writes of the other.
         std::vector<TsvppFrame> f(n);
         for (int i = 0; i < n; ++i) {
             f[i] = frames[i];
             f[i].y = zy[i];
             f[i].uv = zuv[i];
         }
-        rc = convert_batch_impl(ctx, f.data(), n, p, zout.data(), ctx->hstream[0], true);
+        const int nsplit = (n >= 8 && env_int("TSVPP_HOST_SPLIT", 1)) ? 2 : 1;
+        const int half = (n + nsplit - 1) / nsplit;
+        for (int k = 0; k < nsplit; ++k) {
+            const int b0 = k * half, m = std::min(half, n - b0);
+            if (m <= 0) break;
+            rc = convert_batch_impl(ctx, f.data() + b0, m, p, zout.data() + b0, ctx->hstream[k], true);
+            if (rc) break;
+        }
+        cudaError_t e0 = cudaStreamSynchronize(ctx->hstream[0]);
+        cudaError_t e1 = cudaStreamSynchronize(ctx->hstream[1]);
         if (rc) return rc;
-        TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
+        if (e0 != cudaSuccess) return note_error((int)e0, "cudaStreamSynchronize", __LINE__);
+        if (e1 != cudaSuccess) return note_error((int)e1, "cudaStreamSynchronize", __LINE__);
         return TSVPP_OK;
+    }
+    // chunks of frames ping-pong over two streams so that H2D, kernel and D2H overlap
+    const int chunk = std::max(1, std::min(n, env_int("TSVPP_HOST_CHUNK", 16)));
+    for (int s = 0; s < 2; ++s) {
+        if (!zero_copy && ctx->stage_in_cap[s] < in_frame * chunk) {
+            if (ctx->stage_in[s]) cudaFree(ctx->stage_in[s]);
+            ctx->stage_in[s] = nullptr;
+            ctx->stage_in_cap[s] = 0;
+            TSVPP_CUDA(cudaMalloc(&ctx->stage_in[s], in_frame * chunk));
+            ctx->stage_in_cap[s] = in_frame * chunk;
+        }
+        if (!zc_out && ctx->stage_out_cap[s] < out_frame * chunk) {
+            if (ctx->stage_out[s]) cudaFree(ctx->stage_out[s]);
+            ctx->stage_out[s] = nullptr;
+            ctx->stage_out_cap[s] = 0;
+            TSVPP_CUDA(cudaMalloc(&ctx->stage_out[s], out_frame * chunk));
+            ctx->stage_out_cap[s] = out_frame * chunk;
+        }
     }
     std::vector<TsvppFrame> dframes(chunk);
     std::vector<void *> douts(chunk);
@@ -1190,27 +1369,44 @@ int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n,
             douts[k] = zc_out ? zout[base + k] : (void *)(ctx->stage_out[which] + out_frame * k);
         }
         rc = convert_batch_impl(ctx, dframes.data(), m, p, douts.data(), st, zero_copy);
-        if (rc) return rc;
+        if (rc) break;
         if (!zc_out)
             for (int k = 0; k < m; ++k)
                 TSVPP_CUDA(cudaMemcpyAsync(out[base + k], douts[k], elems * es, cudaMemcpyDeviceToHost, st));
         // the staging buffers of this stream are reused two chunks later: the stream order
         // already serialises that, nothing to wait for on the host here
     }
-    TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[0]));
-    TSVPP_CUDA(cudaStreamSynchronize(ctx->hstream[1]));
+    cudaError_t e0 = cudaStreamSynchronize(ctx->hstream[0]);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->hstream[1]);
+    if (rc) return rc;
+    if (e0 != cudaSuccess) return note_error((int)e0, "cudaStreamSynchronize", __LINE__);
+    if (e1 != cudaSuccess) return note_error((int)e1, "cudaStreamSynchronize", __LINE__);
     return TSVPP_OK;
+}
+
+int tsvpp_convert_batch_host(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                             void *const *out) {
+    if (!ctx || !frames || !p || !out || n <= 0) return TSVPP_ERROR;
+    return abi_guard([&]() -> int {
+        TSVPP_ON_DEVICE(ctx);
+        // one host-buffer call at a time per context: it owns the two internal streams and the staging buffers
+        std::lock_guard<std::mutex> lk(ctx->host_mu);
+        return convert_batch_host_impl(ctx, frames, n, p, out);
+    }, __LINE__);
 }
 
 int tsvpp_debug_pow23(const double *w, int n, double *w2, double *w3) {
     if (!w || !w2 || !w3 || n <= 0) return TSVPP_ERROR;
     double *d = nullptr;
     TSVPP_CUDA(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
-    TSVPP_CUDA(cudaMemcpy(d, w, sizeof(double) * n, cudaMemcpyHostToDevice));
-    launch_pow23(d, d + n, d + 2 * (size_t)n, n, 0);
-    TSVPP_CUDA(cudaMemcpy(w2, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    TSVPP_CUDA(cudaMemcpy(w3, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaError_t e = cudaMemcpy(d, w, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_pow23(d, d + n, d + 2 * (size_t)n, n, 0);
+        e = cudaMemcpy(w2, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(w3, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost);
     cudaFree(d);
+    if (e != cudaSuccess) return note_error((int)e, "tsvpp_debug_pow23", __LINE__);
     return TSVPP_OK;
 }
 
@@ -1218,14 +1414,23 @@ int tsvpp_last_host_path(const TsvppContext *ctx) { return ctx ? ctx->last_host_
 
 unsigned long long tsvpp_launch_count(const TsvppContext *ctx) { return ctx ? ctx->launches.load() : 0ull; }
 
+int tsvpp_plan_cache_size(TsvppContext *ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return (int)ctx->plans.size();
+}
+
 int tsvpp_describe_plan(TsvppContext *ctx, const TsvppFrame *f0, const TsvppParams *p, char *buf, size_t buflen) {
     if (!ctx || !f0 || !p || !buf || !buflen) return TSVPP_ERROR;
-    Plan *pl = nullptr;
-    const bool bulk = frames_bulk_ok(f0, 1) && !env_int("TSVPP_FORCE_LDG", 0);
-    int rc = get_plan(ctx, *f0, *p, bulk, &pl);
-    if (rc) return rc;
-    std::snprintf(buf, buflen, "%s", pl->desc.c_str());
-    return TSVPP_OK;
+    return abi_guard([&]() -> int {
+        TSVPP_ON_DEVICE(ctx);
+        std::shared_ptr<Plan> pl;
+        const bool bulk = frames_bulk_ok(f0, 1) && !env_int("TSVPP_FORCE_LDG", 0);
+        int rc = get_plan(ctx, *f0, *p, bulk, &pl);
+        if (rc) return rc;
+        std::snprintf(buf, buflen, "%s", pl->desc.c_str());
+        return TSVPP_OK;
+    }, __LINE__);
 }
 
 }  // extern "C"

@@ -1,0 +1,466 @@
+// vpp_march_kernels.cu -- exact-integer separable resamplers for sm_100a (B200): bicubic and area
+// downscale for geometries whose weights are dyadic rationals (see vpp_march.h for the argument and the
+// work decomposition).  Replaces, for those geometries, the float paths of vpp_kernels.cu that reproduce
+// reference src/Resize.cu:27-91,314-357 (bicubic, FP64) and :160-212,359-386 (area, FP32): same bytes out,
+// 4-6x fewer instructions per output sample.
+//
+//   producer warp : one cp.async.bulk (TMA unit, SASS UBLKCP) per DISTINCT source row a strip touches --
+//                   a row that feeds several output rows is fetched and staged once (the slot-per-tap
+//                   layout of vpp_kernels.cu stages it up to four times).
+//   consumers     : thread = 2 adjacent output columns x the rpg row pairs of its row group.
+//                   bicubic: per newly needed source row and column, 2 aligned shared loads + 1 PRMT give
+//                   the four taps as packed bytes, 2 (or 4) dp4a give the exact horizontal sum, which is
+//                   rounded / clamped like the reference's b0..b3 and shifted into a 4-byte register window;
+//                   each output row is then one more packed dot product of the window.
+//                   area: per window row, funnel-shifted words x packed integer pattern weights (dp4a),
+//                   accumulated with the row's integer weight; one exact division by multiply-shift.
+// Colour conversion, normalisation and the stores are vpp_device.cuh's emit_block, shared with the float path.
+#include "vpp_device.cuh"
+#include "vpp_march.h"
+
+namespace tsvpp {
+
+// u8 x s8 and u8 x u8 four-way dot products with 32-bit accumulate (SASS IDP.4A)
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, int b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a_u8x4, uint32_t b_u8x4, uint32_t c) {
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// clamp(round_half_away(sum_k taps_k * m_k / 2^q), 0, 255) for exact integer weights m_k given as base-128
+// digits -- reference src/Resize.cu:49-51 (`int b = round(a0+a1+a2+a3); min 255; max 0`), whose FP64 sum is
+// exact for such weights.  For s >= 0 round-half-away is floor(s + 1/2); negative sums clamp to 0 either way.
+//   short (q <= 13): m = 128*w[1] + w[0], w[0] in [0,127], w[1] signed
+//   long  (15 <= q <= 27): m = 2^14 * (128*w[3] + w[2]) + (128*w[1] + w[0]), the low part in [0, 16383]:
+//         floor((hi*2^14 + lo + 2^(q-1)) / 2^q) = floor((hi + 2^(q-15) + floor(lo / 2^14)) / 2^(q-14))  (lo >= 0)
+template <bool LONG>
+__device__ __forceinline__ uint32_t idot_round_u8(uint32_t taps, const int (&w)[4], int q) {
+    int r;
+    if constexpr (!LONG) {
+        const int lo = dp4a_us(taps, w[0], 1 << (q - 1));
+        const int hi = dp4a_us(taps, w[1], 0);
+        r = (hi * 128 + lo) >> q;
+    } else {
+        const int lo = dp4a_us(taps, w[1], 0) * 128 + dp4a_us(taps, w[0], 0);
+        const int hi = dp4a_us(taps, w[3], 0) * 128 + dp4a_us(taps, w[2], 1 << (q - 15));
+        r = (hi + (lo >> 14)) >> (q - 14);
+    }
+    return (uint32_t)min(max(r, 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------
+// producer: one bulk copy per distinct source row of the strip
+// ---------------------------------------------------------------------------------------
+struct MarchIter {  // mixed-radix (frame, strip, tile) counter advancing by gridDim.x items
+    int frame, strip, tile;
+    int d_frame, d_strip, d_tile;
+    __device__ __forceinline__ void init(const MarchPlanDev &P, int first, int step) {
+        const int per_frame = P.nstrips * P.ntiles;
+        frame = first / per_frame;
+        const int r = first - frame * per_frame;
+        strip = r / P.ntiles;
+        tile = r - strip * P.ntiles;
+        d_tile = step % P.ntiles;
+        const int q = step / P.ntiles;
+        d_strip = q % P.nstrips;
+        d_frame = q / P.nstrips;
+    }
+    __device__ __forceinline__ void next(const MarchPlanDev &P) {
+        tile += d_tile;
+        int carry = tile >= P.ntiles ? 1 : 0;
+        tile -= carry ? P.ntiles : 0;
+        strip += d_strip + carry;
+        carry = strip >= P.nstrips ? 1 : 0;
+        strip -= carry ? P.nstrips : 0;
+        frame += d_frame + carry;
+    }
+};
+
+template <bool NEED_UV>
+__device__ __forceinline__ void march_fill(const MarchPlanDev &P, const FrameDev *__restrict__ frames,
+                                           const MarchIter &ic, unsigned char *stage, uint64_t *bar, int lane,
+                                           uint64_t policy) {
+    const unsigned long long *fd = reinterpret_cast<const unsigned long long *>(frames + ic.frame);
+    const unsigned char *fy = reinterpret_cast<const unsigned char *>(__ldg(fd));
+    const unsigned char *fuv = reinterpret_cast<const unsigned char *>(__ldg(fd + 1));
+    const int nl = __ldg(P.nslots_l + ic.strip);
+    const int nc = NEED_UV ? __ldg(P.nslots_c + ic.strip) : 0;
+    const int a0l = __ldg(P.seg_a0_l + ic.tile), lenl = __ldg(P.seg_len_l + ic.tile);
+    const int a0c = NEED_UV ? __ldg(P.seg_a0_c + ic.tile) : 0, lenc = NEED_UV ? __ldg(P.seg_len_c + ic.tile) : 0;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nl * lenl + nc * lenc));
+    __syncwarp();
+    fy += a0l;
+    fuv += a0c;
+    const int *rl = P.slotrow_l + (size_t)ic.strip * P.nsl;
+#pragma unroll 4
+    for (int s = 0; s < nl; ++s)
+        bulk_g2s_elected(stage + (size_t)s * P.slot_stride, fy + (size_t)__ldg(rl + s) * P.pitch_y, lenl, bar, policy);
+    if (NEED_UV) {
+        const int *rc = P.slotrow_c + (size_t)ic.strip * P.nsc;
+        unsigned char *sc = stage + (size_t)P.nsl * P.slot_stride;
+#pragma unroll 4
+        for (int s = 0; s < nc; ++s)
+            bulk_g2s_elected(sc + (size_t)s * P.slot_stride, fuv + (size_t)__ldg(rc + s) * P.pitch_uv, lenc, bar, policy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-thread column state
+// ---------------------------------------------------------------------------------------
+template <bool XLONG>
+struct BicubicCols {
+    // two luma columns and one chroma pair
+    int addr0, addr1, addrc;
+    uint32_t sel0, sel1, selcA, selcB;
+    int w0[4], w1[4], wc[4];
+    __device__ __forceinline__ void load(const MarchColB *cl, const MarchColB *cc) {
+        const int4 a0 = __ldg(reinterpret_cast<const int4 *>(cl));
+        const int4 b0 = __ldg(reinterpret_cast<const int4 *>(cl) + 1);
+        const int4 a1 = __ldg(reinterpret_cast<const int4 *>(cl + 1));
+        const int4 b1 = __ldg(reinterpret_cast<const int4 *>(cl + 1) + 1);
+        addr0 = a0.x; sel0 = (uint32_t)a0.y;
+        addr1 = a1.x; sel1 = (uint32_t)a1.y;
+        w0[0] = b0.x; w0[1] = b0.y; w0[2] = b0.z; w0[3] = b0.w;
+        w1[0] = b1.x; w1[1] = b1.y; w1[2] = b1.z; w1[3] = b1.w;
+        if (cc) {
+            const int4 ac = __ldg(reinterpret_cast<const int4 *>(cc));
+            const int4 bc = __ldg(reinterpret_cast<const int4 *>(cc) + 1);
+            addrc = ac.x; selcA = (uint32_t)ac.y; selcB = (uint32_t)ac.z;
+            wc[0] = bc.x; wc[1] = bc.y; wc[2] = bc.z; wc[3] = bc.w;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+// MODE: MARCH_BICUBIC / MARCH_AREA.  VAR: bicubic: XLONG (0/1); area: NW (1, 2 or 4).
+template <int MODE, int VAR, int OK>
+__global__ void __launch_bounds__(kMarchMaxThreads, 2)
+    vpp_march_kernel(const MarchPlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
+    constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NS = P.nstages;
+    unsigned char *stages = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * P.stage_bytes);
+    uint64_t *empty = full + kMaxStages;
+    const int ncons_warps = ((int)blockDim.x >> 5) - 1;
+
+    const int total = nframes * P.nstrips * P.ntiles;
+    const int first = blockIdx.x;
+    const int my_items = first < total ? (total - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full + s, 1u);
+            mbar_init(empty + s, (uint32_t)ncons_warps);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= producer =================
+        const uint64_t policy = l2_policy_evict_first();
+        MarchIter ic;
+        ic.init(P, first, (int)gridDim.x);
+        int s = 0;
+        uint32_t phase = 1;  // a fresh "empty" barrier passes a wait on parity 1
+        for (int it = 0; it < my_items; ++it, ic.next(P)) {
+            mbar_wait(empty + s, phase);
+            march_fill<NEED_UV>(P, frames, ic, stages + (size_t)s * P.stage_bytes, full + s, lane, policy);
+            if (++s == NS) {
+                s = 0;
+                phase ^= 1u;
+            }
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const int ctid = tid - 32;
+    const int blocks_x = P.tw >> 1;
+    const int tx = ctid % blocks_x;  // column block inside the tile
+    const int g = ctid / blocks_x;   // row group inside the strip
+    const bool active = g < P.G;
+    const bool vec = vec_ok != 0;
+    const int R2 = P.G * P.rpg;      // row pairs per strip
+    const uint32_t sbase = smem_base_laundered();
+    const uint32_t sstride = (uint32_t)P.slot_stride;
+
+    int cur_tile = -1;
+    // per-tile column state
+    BicubicCols<(MODE == MARCH_BICUBIC) && (VAR != 0)> bc;
+    int a_addr0 = 0, a_addr1 = 0, a_addrc = 0, a_sh0 = 0, a_sh1 = 0, a_shc = 0, a_pr0 = 0, a_pr1 = 0, a_prc = 0;
+    constexpr int NW = (MODE == MARCH_AREA) ? VAR : 1;
+    uint32_t a_w0[NW], a_w1[NW], a_wc[NW];
+
+    MarchIter ic;
+    ic.init(P, first, (int)gridDim.x);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < my_items; ++it, ic.next(P)) {
+        const uint32_t stage = sbase + (uint32_t)(s * P.stage_bytes);
+        const uint32_t stage_c = stage + (uint32_t)P.nsl * sstride;
+        const int j0 = ic.tile * P.tw + 2 * tx;
+        const bool have_c = NEED_UV && (j0 >> 1) < P.e.cw2;
+        if (active && ic.tile != cur_tile) {
+            cur_tile = ic.tile;
+            const int cidx = ic.tile * P.tw + 2 * tx;  // tables are padded to ntiles*tw columns
+            if constexpr (MODE == MARCH_BICUBIC) {
+                const MarchColB *cl = reinterpret_cast<const MarchColB *>(P.col_l) + cidx;
+                const MarchColB *cc = NEED_UV ? reinterpret_cast<const MarchColB *>(P.col_c) + (cidx >> 1) : nullptr;
+                bc.load(cl, cc);
+            } else {
+                const MarchColA *cl = reinterpret_cast<const MarchColA *>(P.col_l) + cidx;
+                const int4 c0 = __ldg(reinterpret_cast<const int4 *>(cl));
+                const int4 c1 = __ldg(reinterpret_cast<const int4 *>(cl + 1));
+                a_addr0 = c0.x; a_sh0 = c0.y; a_pr0 = c0.z;
+                a_addr1 = c1.x; a_sh1 = c1.y; a_pr1 = c1.z;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    a_w0[k] = (uint32_t)__ldg(P.px_w + a_pr0 * NW + k);
+                    a_w1[k] = (uint32_t)__ldg(P.px_w + a_pr1 * NW + k);
+                }
+                if (NEED_UV) {
+                    const int4 cc = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const MarchColA *>(P.col_c) + (cidx >> 1)));
+                    a_addrc = cc.x; a_shc = cc.y; a_prc = cc.z;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) a_wc[k] = (uint32_t)__ldg(P.px_w + a_prc * NW + k);
+                }
+            }
+        }
+
+        mbar_wait(full + s, phase);
+
+        if (active) {
+            const int pr0 = ic.strip * R2 + g * P.rpg;  // first row pair (global index) of this thread's group
+            void *outp = frames[ic.frame].out;
+            if constexpr (MODE == MARCH_BICUBIC) {
+                constexpr bool XL = VAR != 0;
+                const MarchRowB *rowl = reinterpret_cast<const MarchRowB *>(P.row_l);
+                const MarchRowB *rowc = reinterpret_cast<const MarchRowB *>(P.row_c);
+                // windows of the last four marched slots: byte 3 = newest
+                uint32_t WY0 = 0, WY1 = 0, WU = 0, WV = 0;
+                int curl = __ldg(&rowl[2 * pr0].first) - 1;
+                int curc = NEED_UV ? __ldg(&rowc[pr0].first) - 1 : 0;
+                for (int p = 0; p < P.rpg; ++p) {
+                    const int pr = pr0 + p;
+                    const int i0 = 2 * pr;
+                    if (i0 >= P.e.dh) break;  // uniform: rows past the image
+                    int Yv[2][2];
+                    int UV[1][2] = {{0, 0}};
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const int4 r0 = __ldg(reinterpret_cast<const int4 *>(rowl + i0 + a));
+                        const int4 r1 = __ldg(reinterpret_cast<const int4 *>(rowl + i0 + a) + 1);
+                        const int newest = r0.y;
+                        const int wv[4] = {r1.x, r1.y, r1.z, r1.w};
+                        while (curl < newest) {  // uniform trip count
+                            ++curl;
+                            const uint32_t sl = stage + (uint32_t)curl * sstride;
+                            const uint32_t t0 = __byte_perm(lds32(sl + bc.addr0), lds32(sl + bc.addr0 + 4), bc.sel0);
+                            const uint32_t t1 = __byte_perm(lds32(sl + bc.addr1), lds32(sl + bc.addr1 + 4), bc.sel1);
+                            const uint32_t h0 = idot_round_u8<XL>(t0, bc.w0, P.qx);
+                            const uint32_t h1 = idot_round_u8<XL>(t1, bc.w1, P.qx);
+                            WY0 = __byte_perm(WY0, h0, 0x4321);
+                            WY1 = __byte_perm(WY1, h1, 0x4321);
+                        }
+                        if (P.ylong) {
+                            Yv[a][0] = (int)idot_round_u8<true>(WY0, wv, P.qy);
+                            Yv[a][1] = (int)idot_round_u8<true>(WY1, wv, P.qy);
+                        } else {
+                            Yv[a][0] = (int)idot_round_u8<false>(WY0, wv, P.qy);
+                            Yv[a][1] = (int)idot_round_u8<false>(WY1, wv, P.qy);
+                        }
+                    }
+                    if (NEED_UV && pr < P.e.ch2) {
+                        const int4 r0 = __ldg(reinterpret_cast<const int4 *>(rowc + pr));
+                        const int4 r1 = __ldg(reinterpret_cast<const int4 *>(rowc + pr) + 1);
+                        const int newest = r0.y;
+                        const int wv[4] = {r1.x, r1.y, r1.z, r1.w};
+                        while (curc < newest) {
+                            ++curc;
+                            const uint32_t sl = stage_c + (uint32_t)curc * sstride + (uint32_t)bc.addrc;
+                            const uint32_t x0 = lds32(sl), x1 = lds32(sl + 4), x2 = lds32(sl + 8);
+                            const uint32_t tu = __byte_perm(__byte_perm(x0, x1, bc.selcA & 0xffffu), x2, bc.selcB & 0xffffu);
+                            const uint32_t tv = __byte_perm(__byte_perm(x0, x1, bc.selcA >> 16), x2, bc.selcB >> 16);
+                            WU = __byte_perm(WU, idot_round_u8<XL>(tu, bc.wc, P.qx), 0x4321);
+                            WV = __byte_perm(WV, idot_round_u8<XL>(tv, bc.wc, P.qx), 0x4321);
+                        }
+                        if (have_c) {
+                            if (P.ylong) {
+                                UV[0][0] = (int)idot_round_u8<true>(WU, wv, P.qy);
+                                UV[0][1] = (int)idot_round_u8<true>(WV, wv, P.qy);
+                            } else {
+                                UV[0][0] = (int)idot_round_u8<false>(WU, wv, P.qy);
+                                UV[0][1] = (int)idot_round_u8<false>(WV, wv, P.qy);
+                            }
+                        }
+                    }
+                    const int nx = min(2, P.e.dw - j0), ny = min(2, P.e.dh - i0);
+                    if (nx > 0) {
+                        if (nx == 2 && ny == 2 && vec)
+                            emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, 2, 2, true);
+                        else
+                            emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
+                    }
+                }
+            } else {
+                // ---- area ----
+                const MarchRowA *rowl = reinterpret_cast<const MarchRowA *>(P.row_l);
+                const MarchRowA *rowc = reinterpret_cast<const MarchRowA *>(P.row_c);
+                const int K = P.K;
+                for (int p = 0; p < P.rpg; ++p) {
+                    const int pr = pr0 + p;
+                    const int i0 = 2 * pr;
+                    if (i0 >= P.e.dh) break;
+                    int Yv[2][2];
+                    int UV[1][2] = {{0, 0}};
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const int2 ra = __ldg(reinterpret_cast<const int2 *>(rowl + i0 + a));
+                        const int *pyw = P.py_w + ra.y * K;
+                        uint32_t acc0 = 0, acc1 = 0;
+                        uint32_t sl = stage + (uint32_t)ra.x * sstride;
+                        for (int k = 0; k < K; ++k, sl += sstride) {
+                            const uint32_t wy = (uint32_t)__ldg(pyw + k);
+                            if (wy == 0) continue;  // zero padding of the pattern row (uniform)
+                            uint32_t h0 = 0, h1 = 0;
+                            uint32_t lo0 = lds32(sl + a_addr0), lo1 = lds32(sl + a_addr1);
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) {
+                                const uint32_t hi0 = lds32(sl + a_addr0 + 4 * (w + 1));
+                                const uint32_t hi1 = lds32(sl + a_addr1 + 4 * (w + 1));
+                                h0 = dp4a_uu(__funnelshift_r(lo0, hi0, a_sh0), a_w0[w], h0);
+                                h1 = dp4a_uu(__funnelshift_r(lo1, hi1, a_sh1), a_w1[w], h1);
+                                lo0 = hi0;
+                                lo1 = hi1;
+                            }
+                            acc0 += wy * h0;
+                            acc1 += wy * h1;
+                        }
+                        const int dj0 = ra.y * P.PX + a_pr0, dj1 = ra.y * P.PX + a_pr1;
+                        Yv[a][0] = (int)(__umulhi(acc0, __ldg(P.div_mul + dj0)) >> __ldg(P.div_shift + dj0));
+                        Yv[a][1] = (int)(__umulhi(acc1, __ldg(P.div_mul + dj1)) >> __ldg(P.div_shift + dj1));
+                    }
+                    if (NEED_UV && pr < P.e.ch2 && have_c) {
+                        const int2 ra = __ldg(reinterpret_cast<const int2 *>(rowc + pr));
+                        const int *pyw = P.py_w + ra.y * K;
+                        uint32_t accu = 0, accv = 0;
+                        uint32_t sl = stage_c + (uint32_t)ra.x * sstride + (uint32_t)a_addrc;
+                        for (int k = 0; k < K; ++k, sl += sstride) {
+                            const uint32_t wy = (uint32_t)__ldg(pyw + k);
+                            if (wy == 0) continue;
+                            uint32_t hu = 0, hv = 0;
+                            uint32_t lo = lds32(sl);
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) {
+                                const uint32_t m1 = lds32(sl + 8 * w + 4), m2 = lds32(sl + 8 * w + 8);
+                                const uint32_t x0 = __funnelshift_r(lo, m1, a_shc), x1 = __funnelshift_r(m1, m2, a_shc);
+                                hu = dp4a_uu(__byte_perm(x0, x1, 0x6420), a_wc[w], hu);  // U bytes of 4 pairs
+                                hv = dp4a_uu(__byte_perm(x0, x1, 0x7531), a_wc[w], hv);  // V bytes
+                                lo = m2;
+                            }
+                            accu += wy * hu;
+                            accv += wy * hv;
+                        }
+                        const int dj = ra.y * P.PX + a_prc;
+                        const uint32_t mul = __ldg(P.div_mul + dj);
+                        const int sh = __ldg(P.div_shift + dj);
+                        UV[0][0] = (int)(__umulhi(accu, mul) >> sh);
+                        UV[0][1] = (int)(__umulhi(accv, mul) >> sh);
+                    }
+                    const int nx = min(2, P.e.dw - j0), ny = min(2, P.e.dh - i0);
+                    if (nx > 0) {
+                        if (nx == 2 && ny == 2 && vec)
+                            emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, 2, 2, true);
+                        else
+                            emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
+                    }
+                }
+            }
+        }
+        // all shared-memory reads of this stage are done: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        if (++s == NS) {
+            s = 0;
+            phase ^= 1u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------
+using MarchFn = void (*)(const MarchPlanDev, const FrameDev *, int, int);
+
+template <int MODE, int VAR>
+static MarchFn pick_ok(int ok) {
+    switch (ok) {
+        case OUT_RGB_PLANAR_U8: return vpp_march_kernel<MODE, VAR, OUT_RGB_PLANAR_U8>;
+        case OUT_RGB_PLANAR_F32: return vpp_march_kernel<MODE, VAR, OUT_RGB_PLANAR_F32>;
+        case OUT_RGB_MERGED_U8: return vpp_march_kernel<MODE, VAR, OUT_RGB_MERGED_U8>;
+        case OUT_RGB_MERGED_F32: return vpp_march_kernel<MODE, VAR, OUT_RGB_MERGED_F32>;
+        case OUT_Y800_U8: return vpp_march_kernel<MODE, VAR, OUT_Y800_U8>;
+        case OUT_Y800_F32: return vpp_march_kernel<MODE, VAR, OUT_Y800_F32>;
+        case OUT_HSV_F32: return vpp_march_kernel<MODE, VAR, OUT_HSV_F32>;
+        case OUT_NV12_U8: return vpp_march_kernel<MODE, VAR, OUT_NV12_U8>;
+        case OUT_NV12_F32: return vpp_march_kernel<MODE, VAR, OUT_NV12_F32>;
+    }
+    return nullptr;
+}
+static MarchFn pick_march(const MarchPlanDev &P, int ok) {
+    if (P.mode == MARCH_BICUBIC) return P.xlong ? pick_ok<MARCH_BICUBIC, 1>(ok) : pick_ok<MARCH_BICUBIC, 0>(ok);
+    switch (P.NW) {
+        case 1: return pick_ok<MARCH_AREA, 1>(ok);
+        case 2: return pick_ok<MARCH_AREA, 2>(ok);
+        case 4: return pick_ok<MARCH_AREA, 4>(ok);
+    }
+    return nullptr;
+}
+
+int march_block_threads(const MarchPlanDev &P) {
+    const int cons = (P.tw / 2) * P.G;
+    return 32 + (cons + 31) / 32 * 32;
+}
+size_t march_smem_bytes(const MarchPlanDev &P) { return (size_t)P.nstages * P.stage_bytes + 2 * 8 * kMaxStages + 128; }
+
+int configure_march(const MarchPlanDev &P, int ok, size_t smem_optin_max) {
+    MarchFn fn = pick_march(P, ok);
+    if (!fn) return (int)cudaErrorMissingConfiguration;
+    return (int)cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_optin_max);
+}
+int march_max_ctas_per_sm(const MarchPlanDev &P, int ok, int threads, size_t smem_bytes) {
+    MarchFn fn = pick_march(P, ok);
+    if (!fn) return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reinterpret_cast<const void *>(fn), threads, smem_bytes) !=
+        cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int launch_march(const MarchPlanDev &P, int ok, const FrameDev *frames_dev, int nframes, int vec_ok, int grid,
+                 size_t smem_bytes, cudaStream_t stream) {
+    MarchFn fn = pick_march(P, ok);
+    if (!fn) return (int)cudaErrorMissingConfiguration;
+    fn<<<grid, march_block_threads(P), smem_bytes, stream>>>(P, frames_dev, nframes, vec_ok);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace tsvpp
