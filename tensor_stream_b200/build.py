@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtsvpp.so")
 
-SOURCES = ["vpp_kernels.cu", "vpp_yuv_kernels.cu", "tsvpp_capi.cpp", "VideoProcessor.cpp"]
-HEADERS = ["vpp_plan.h", "vpp_launch.h", "../../include/tsvpp.h", "../../include/VideoProcessor.h",
+SOURCES = ["vpp_kernels.cu", "vpp_march_kernels.cu", "vpp_yuv_kernels.cu", "tsvpp_capi.cpp", "VideoProcessor.cpp"]
+HEADERS = ["vpp_plan.h", "vpp_launch.h", "vpp_device.cuh", "vpp_march.h", "march_plan.inl", "../../include/tsvpp.h", "../../include/VideoProcessor.h",
            "../../include/tsvpp_avframe.h"]
 
 NVCC_FLAGS = [
@@ -36,15 +36,18 @@ def build(force=False, verbose=False):
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if not force and not _stale(LIB, deps):
         return LIB
-    objs = []
-    for s in srcs:
+    objs, procs = [], []
+    for s in srcs:  # the translation units compile in parallel
         o = os.path.join(CSRC, os.path.basename(s) + ".o")
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         if s.endswith(".cpp"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")
-        subprocess.check_call(cmd)
+        procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(o)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
     subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcuda"])
     for o in objs:
         os.remove(o)

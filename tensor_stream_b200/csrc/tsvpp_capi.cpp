@@ -25,6 +25,7 @@
 
 #include "../../include/tsvpp.h"
 #include "vpp_launch.h"
+#include "vpp_march.h"
 #include "vpp_plan.h"
 
 using namespace tsvpp;
@@ -303,10 +304,20 @@ struct Plan {
     long fetch_bytes_per_frame = 0;
     void *dev_tables = nullptr;
     std::string desc;
+    // exact-integer separable kernel (vpp_march_kernels.cu), used instead of the float kernel when the
+    // geometry's weights are dyadic (march_plan.inl)
+    bool march = false;
+    MarchPlanDev mdev{};
+    void *march_tables = nullptr;
+    size_t march_smem = 0;
+    int march_ctas_per_sm = 1;
     ~Plan() {
         if (dev_tables) cudaFree(dev_tables);
+        if (march_tables) cudaFree(march_tables);
     }
 };
+
+#include "march_plan.inl"
 
 }  // namespace
 
@@ -319,6 +330,7 @@ struct TsvppContext {
     std::map<PlanKey, std::shared_ptr<Plan>> plans;
     std::list<PlanKey> lru;  // most recently used first
     size_t max_plans = 64;
+    bool no_march = false;  // TSVPP_NO_MARCH=1 at tsvpp_create: keep the float bicubic / area kernels (A/B, tests)
     std::atomic<unsigned long long> launches{0};
     // descriptor ring for tsvpp_convert_batch (pinned host + device), guarded by events
     static constexpr int kRing = 32;  // concurrent convert calls in flight (the reference allows maxConsumers = 5 by default)
@@ -836,6 +848,32 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
                   rs_names[rs], ok, bulk ? "bulk" : "ldg", bw, tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
                   nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize, fetch, D.direct);
     pl->desc = buf;
+    if (bulk && (rs == RS_BICUBIC || rs == RS_AREA) && !ctx->no_march) {
+        MarchInputs mi;
+        mi.g = g; mi.rs = rs; mi.ok = ok; mi.need_uv = need_uv;
+        mi.W = W; mi.H = H; mi.pitch_y = pitch_y; mi.pitch_uv = pitch_uv;
+        mi.dw = dw; mi.dh = dh; mi.cw2 = cw2; mi.ch2 = ch2; mi.swap_rb = D.swap_rb;
+        mi.xs = &xs; mi.ys = &ys; mi.tap_l = &tap_l; mi.tap_c = &tap_c; mi.lo_c = &lo_c;
+        mi.lo_l = &lo_l; mi.hi_l = &hi_l; mi.hi_c = &hi_c;
+        mi.cxw = &cxw; mi.cyw = &cyw;
+        mi.K = K; mi.KX = KX; mi.PX = PX; mi.PY = PY; mi.patx = &patx; mi.paty = &paty;
+        mi.smem_cap = smem_cap;
+        MarchPlanHost mh;
+        const int mrc = build_march(mi, ctx->sm_count, mh);
+        if (mrc == TSVPP_OK) {
+            pl->march = true;
+            pl->mdev = mh.dev;
+            pl->march_tables = mh.dev_tables;
+            pl->march_smem = mh.smem;
+            pl->march_ctas_per_sm = cap_ctas > 0 ? std::min(mh.ctas_per_sm, cap_ctas) : mh.ctas_per_sm;
+            pl->fetch_bytes_per_frame = mh.fetch_bytes_per_frame;
+            pl->vec_ok_geom = (dw % 2 == 0) ? 1 : 0;
+            pl->desc = mh.desc;
+        } else {
+            if (mh.dev_tables) cudaFree(mh.dev_tables);
+            if (mrc > 0) return mrc;  // a CUDA error, not "not eligible"
+        }
+    }
     out = std::move(pl);
     return TSVPP_OK;
 }
@@ -914,17 +952,19 @@ int vec_ok_for(const Plan *pl, void *const *out, int n) {
 // device-resident frames of a no-resize plan skip the staging ring (vpp_direct_kernel)
 int launch_plan(const Plan *pl, const FrameDev *frames_dev, int n, int vec_ok, int grid, cudaStream_t stream,
                 bool allow_direct) {
+    if (pl->march) return launch_march(pl->mdev, pl->ok, frames_dev, n, vec_ok, grid, pl->march_smem, stream);
     if (pl->dev.direct && allow_direct) return launch_direct(pl->ok, pl->dev, frames_dev, n, vec_ok, stream);
     return launch_fused(pl->rs, pl->ok, pl->bulk, pl->dev, frames_dev, n, vec_ok, grid, pl->smem, stream);
 }
 
 int grid_for(const TsvppContext *ctx, const Plan *pl, int n) {
-    const long items = (long)n * pl->dev.nstrips * pl->dev.ntiles;
-    long cap = (long)ctx->sm_count * pl->ctas_per_sm;
+    const int ntiles = pl->march ? pl->mdev.ntiles : pl->dev.ntiles;
+    const long items = (long)n * (pl->march ? pl->mdev.nstrips : pl->dev.nstrips) * ntiles;
+    long cap = (long)ctx->sm_count * (pl->march ? pl->march_ctas_per_sm : pl->ctas_per_sm);
     // a CTA's items advance by gridDim.x and the tile is the fastest-varying item coordinate: with
     // the grid a multiple of ntiles every CTA keeps ONE column tile for its whole life, so its
     // column tap tables are loaded once instead of once per item
-    if (cap > pl->dev.ntiles) cap -= cap % pl->dev.ntiles;
+    if (cap > ntiles) cap -= cap % ntiles;
     return (int)std::max(1L, std::min(items, cap));
 }
 
@@ -955,6 +995,7 @@ int tsvpp_create(int device, TsvppContext **out) {
         TSVPP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         c->smem_optin = (size_t)v;
         c->max_plans = (size_t)std::max(1, env_int("TSVPP_MAX_PLANS", 64));
+        c->no_march = env_int("TSVPP_NO_MARCH", 0) != 0;
         *out = c.release();
         return TSVPP_OK;
     }, __LINE__);

@@ -18,6 +18,9 @@
 //   area:    per source row of the window a horizontal dot of KX bytes with the integer pattern row, weighted
 //            into an integer accumulator; one exact division at the end (src/Resize.cu:160-178).
 #pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
 #include <cstdint>
 
 #include "vpp_plan.h"
@@ -34,7 +37,8 @@ struct MarchColB {
     unsigned sel0;  // luma: PRMT selector picking the 4 taps out of {w0,w1}.
                     // chroma: selA of U (low 16 bits) and of V (high 16): picks from {w0,w1}
     unsigned sel1;  // chroma: selB of U / V: merges the first pick with w2
-    int pad;
+    int exact;      // 1: the FP64 weights ARE m / 2^q; 0: they are within 2^-44 of it (libdevice pow is not correctly
+                    // rounded): sums that land exactly on a .5 tie are then re-evaluated with the FP64 chain
     int w[4];       // weight digits, base 128 (short: w[0] low, w[1] high; long: w[0..1] = (m & 16383), w[2..3] = m >> 14)
 };
 // area: one record per luma column and one per chroma pair
@@ -48,7 +52,8 @@ struct MarchColA {
 struct MarchRowB {
     int first;   // strip-relative slot of the oldest tap
     int newest;  // strip-relative slot of the newest tap: slots up to here must have been marched
-    int pad[2];
+    unsigned tapsel;  // PRMT selector that rebuilds the four taps (in tap order) from the window, for the FP64 tie path
+    int exact;
     int w[4];    // vertical weight digits, folded onto the window bytes (byte 3 = slot `newest`)
 };
 // area: per output row
@@ -78,6 +83,8 @@ struct MarchPlanDev {
     const int *nslots_l, *nslots_c;                          // [nstrips]
     const void *col_l, *col_c;                               // [ntiles*tw] / [ntiles*tw/2]
     const void *row_l, *row_c;                               // [nstrips*R] / [nstrips*R/2]
+    const double *cxd;                                       // bicubic: [dw][4] the reference's FP64 horizontal weights
+    const double *cyd;                                       // bicubic: [dh][4] vertical ones (row i; chroma row ci uses row ci)
     const int *px_w;                                         // area: [PX][NW] packed u8 weights
     const int *py_w;                                         // area: [PY][K] integer weights
     const unsigned *div_mul;                                 // area: [PY][PX] magic multiplier of the divisor

@@ -37,25 +37,47 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
-// clamp(round_half_away(sum_k taps_k * m_k / 2^q), 0, 255) for exact integer weights m_k given as base-128
-// digits -- reference src/Resize.cu:49-51 (`int b = round(a0+a1+a2+a3); min 255; max 0`), whose FP64 sum is
-// exact for such weights.  For s >= 0 round-half-away is floor(s + 1/2); negative sums clamp to 0 either way.
+// clamp(round_half_away(sum_k taps_k * m_k / 2^q), 0, 255) for integer weights m_k given as base-128
+// digits -- reference src/Resize.cu:49-51 (`int b = round(a0+a1+a2+a3); min 255; max 0`).  For s >= 0
+// round-half-away is floor(s + 1/2); negative sums clamp to 0 either way.
 //   short (q <= 13): m = 128*w[1] + w[0], w[0] in [0,127], w[1] signed
 //   long  (15 <= q <= 27): m = 2^14 * (128*w[3] + w[2]) + (128*w[1] + w[0]), the low part in [0, 16383]:
 //         floor((hi*2^14 + lo + 2^(q-1)) / 2^q) = floor((hi + 2^(q-15) + floor(lo / 2^14)) / 2^(q-14))  (lo >= 0)
+// `tie` reports a sum whose fraction is exactly one half.  The reference's FP64 weights come out of libdevice's
+// pow(), which is not correctly rounded: they can sit a few 1e-17 off the dyadic values m / 2^q.  That moves
+// the FP64 sum by < 1e-12, which changes round() only where the exact sum is a tie -- every other multiple of
+// 2^-q is at least 2^-27 away from one.  Ties of inexact weights are re-evaluated with the reference's own
+// FP64 chain (bicubic_dot); everything else is exact by construction.
 template <bool LONG>
-__device__ __forceinline__ uint32_t idot_round_u8(uint32_t taps, const int (&w)[4], int q) {
+__device__ __forceinline__ uint32_t idot_round_u8(uint32_t taps, const int (&w)[4], int q, bool &tie) {
     int r;
     if constexpr (!LONG) {
         const int lo = dp4a_us(taps, w[0], 1 << (q - 1));
         const int hi = dp4a_us(taps, w[1], 0);
-        r = (hi * 128 + lo) >> q;
+        const int t = hi * 128 + lo;
+        tie = (t & ((1 << q) - 1)) == 0;
+        r = t >> q;
     } else {
         const int lo = dp4a_us(taps, w[1], 0) * 128 + dp4a_us(taps, w[0], 0);
         const int hi = dp4a_us(taps, w[3], 0) * 128 + dp4a_us(taps, w[2], 1 << (q - 15));
-        r = (hi + (lo >> 14)) >> (q - 14);
+        const int u = hi + (lo >> 14);
+        tie = ((lo & 16383) == 0) && ((u & ((1 << (q - 14)) - 1)) == 0);
+        r = u >> (q - 14);
     }
     return (uint32_t)min(max(r, 0), 255);
+}
+// the tie path: reference src/Resize.cu:45-51 with its FP64 weights (taps in tap order, one per byte)
+__device__ __noinline__ uint32_t bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps) {
+    return (uint32_t)bicubic_dot(c[0], c[1], c[2], c[3], (int)(taps & 0xffu), (int)((taps >> 8) & 0xffu),
+                                 (int)((taps >> 16) & 0xffu), (int)(taps >> 24));
+}
+template <bool LONG>
+__device__ __forceinline__ uint32_t bicubic_sum_u8(uint32_t taps, const int (&w)[4], int q, int exact,
+                                                   const double *__restrict__ cd) {
+    bool tie;
+    uint32_t r = idot_round_u8<LONG>(taps, w, q, tie);
+    if (tie && !exact) r = bicubic_tie_fp64(cd, taps);
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -122,20 +144,21 @@ struct BicubicCols {
     // two luma columns and one chroma pair
     int addr0, addr1, addrc;
     uint32_t sel0, sel1, selcA, selcB;
+    int ex0, ex1, exc;  // weights exactly dyadic (no FP64 tie path)
     int w0[4], w1[4], wc[4];
     __device__ __forceinline__ void load(const MarchColB *cl, const MarchColB *cc) {
         const int4 a0 = __ldg(reinterpret_cast<const int4 *>(cl));
         const int4 b0 = __ldg(reinterpret_cast<const int4 *>(cl) + 1);
         const int4 a1 = __ldg(reinterpret_cast<const int4 *>(cl + 1));
         const int4 b1 = __ldg(reinterpret_cast<const int4 *>(cl + 1) + 1);
-        addr0 = a0.x; sel0 = (uint32_t)a0.y;
-        addr1 = a1.x; sel1 = (uint32_t)a1.y;
+        addr0 = a0.x; sel0 = (uint32_t)a0.y; ex0 = a0.w;
+        addr1 = a1.x; sel1 = (uint32_t)a1.y; ex1 = a1.w;
         w0[0] = b0.x; w0[1] = b0.y; w0[2] = b0.z; w0[3] = b0.w;
         w1[0] = b1.x; w1[1] = b1.y; w1[2] = b1.z; w1[3] = b1.w;
         if (cc) {
             const int4 ac = __ldg(reinterpret_cast<const int4 *>(cc));
             const int4 bc = __ldg(reinterpret_cast<const int4 *>(cc) + 1);
-            addrc = ac.x; selcA = (uint32_t)ac.y; selcB = (uint32_t)ac.z;
+            addrc = ac.x; selcA = (uint32_t)ac.y; selcB = (uint32_t)ac.z; exc = ac.w;
             wc[0] = bc.x; wc[1] = bc.y; wc[2] = bc.z; wc[3] = bc.w;
         }
     }
@@ -251,6 +274,15 @@ __global__ void __launch_bounds__(kMarchMaxThreads, 2)
                 constexpr bool XL = VAR != 0;
                 const MarchRowB *rowl = reinterpret_cast<const MarchRowB *>(P.row_l);
                 const MarchRowB *rowc = reinterpret_cast<const MarchRowB *>(P.row_c);
+                const double *cxd = P.cxd, *cyd = P.cyd;
+                const int qy = P.qy, ylong = P.ylong;
+                // vertical sum of a window; `tapsel` puts the window bytes back into tap order for the tie path
+                auto vsum = [&](uint32_t Wn, const int (&wv)[4], uint32_t tapsel, int exact, const double *cd) -> uint32_t {
+                    bool tie;
+                    uint32_t r = ylong ? idot_round_u8<true>(Wn, wv, qy, tie) : idot_round_u8<false>(Wn, wv, qy, tie);
+                    if (tie && !exact) r = bicubic_tie_fp64(cd, __byte_perm(Wn, 0u, tapsel));
+                    return r;
+                };
                 // windows of the last four marched slots: byte 3 = newest
                 uint32_t WY0 = 0, WY1 = 0, WU = 0, WV = 0;
                 int curl = __ldg(&rowl[2 * pr0].first) - 1;
@@ -272,18 +304,13 @@ __global__ void __launch_bounds__(kMarchMaxThreads, 2)
                             const uint32_t sl = stage + (uint32_t)curl * sstride;
                             const uint32_t t0 = __byte_perm(lds32(sl + bc.addr0), lds32(sl + bc.addr0 + 4), bc.sel0);
                             const uint32_t t1 = __byte_perm(lds32(sl + bc.addr1), lds32(sl + bc.addr1 + 4), bc.sel1);
-                            const uint32_t h0 = idot_round_u8<XL>(t0, bc.w0, P.qx);
-                            const uint32_t h1 = idot_round_u8<XL>(t1, bc.w1, P.qx);
+                            const uint32_t h0 = bicubic_sum_u8<XL>(t0, bc.w0, P.qx, bc.ex0, cxd + 4 * (size_t)j0);
+                            const uint32_t h1 = bicubic_sum_u8<XL>(t1, bc.w1, P.qx, bc.ex1, cxd + 4 * (size_t)(j0 + 1));
                             WY0 = __byte_perm(WY0, h0, 0x4321);
                             WY1 = __byte_perm(WY1, h1, 0x4321);
                         }
-                        if (P.ylong) {
-                            Yv[a][0] = (int)idot_round_u8<true>(WY0, wv, P.qy);
-                            Yv[a][1] = (int)idot_round_u8<true>(WY1, wv, P.qy);
-                        } else {
-                            Yv[a][0] = (int)idot_round_u8<false>(WY0, wv, P.qy);
-                            Yv[a][1] = (int)idot_round_u8<false>(WY1, wv, P.qy);
-                        }
+                        Yv[a][0] = (int)vsum(WY0, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)(i0 + a));
+                        Yv[a][1] = (int)vsum(WY1, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)(i0 + a));
                     }
                     if (NEED_UV && pr < P.e.ch2) {
                         const int4 r0 = __ldg(reinterpret_cast<const int4 *>(rowc + pr));
@@ -296,17 +323,13 @@ __global__ void __launch_bounds__(kMarchMaxThreads, 2)
                             const uint32_t x0 = lds32(sl), x1 = lds32(sl + 4), x2 = lds32(sl + 8);
                             const uint32_t tu = __byte_perm(__byte_perm(x0, x1, bc.selcA & 0xffffu), x2, bc.selcB & 0xffffu);
                             const uint32_t tv = __byte_perm(__byte_perm(x0, x1, bc.selcA >> 16), x2, bc.selcB >> 16);
-                            WU = __byte_perm(WU, idot_round_u8<XL>(tu, bc.wc, P.qx), 0x4321);
-                            WV = __byte_perm(WV, idot_round_u8<XL>(tv, bc.wc, P.qx), 0x4321);
+                            // chroma pair cj = j0/2 uses the horizontal weights of luma column cj (src/Resize.cu:351-353)
+                            WU = __byte_perm(WU, bicubic_sum_u8<XL>(tu, bc.wc, P.qx, bc.exc, cxd + 4 * (size_t)(j0 >> 1)), 0x4321);
+                            WV = __byte_perm(WV, bicubic_sum_u8<XL>(tv, bc.wc, P.qx, bc.exc, cxd + 4 * (size_t)(j0 >> 1)), 0x4321);
                         }
                         if (have_c) {
-                            if (P.ylong) {
-                                UV[0][0] = (int)idot_round_u8<true>(WU, wv, P.qy);
-                                UV[0][1] = (int)idot_round_u8<true>(WV, wv, P.qy);
-                            } else {
-                                UV[0][0] = (int)idot_round_u8<false>(WU, wv, P.qy);
-                                UV[0][1] = (int)idot_round_u8<false>(WV, wv, P.qy);
-                            }
+                            UV[0][0] = (int)vsum(WU, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)pr);
+                            UV[0][1] = (int)vsum(WV, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)pr);
                         }
                     }
                     const int nx = min(2, P.e.dw - j0), ny = min(2, P.e.dh - i0);

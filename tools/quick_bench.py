@@ -37,6 +37,12 @@ def main():
     elif cfg == "area":
         cfgs = [("area 256 bgr planar f32", vpp.FrameParameters(256, 256, resize_type=vpp.ResizeType.AREA,
                  pixel_format=vpp.FourCC.BGR24, planes_pos=vpp.Planes.PLANAR, normalization=True))]
+    elif cfg.startswith("x:"):
+        # x:<resize>:<dw>x<dh>:<fourcc>:<planes>:<f32|u8>, e.g. x:AREA:128x128:BGR24:PLANAR:f32
+        _, rt, dst, fcc, pl, ty = cfg.split(":")
+        dw_, dh_ = (int(v) for v in dst.split("x"))
+        cfgs = [(cfg, vpp.FrameParameters(dw_, dh_, resize_type=getattr(vpp.ResizeType, rt), pixel_format=getattr(vpp.FourCC, fcc),
+                                          planes_pos=getattr(vpp.Planes, pl), normalization=(ty == "f32")))]
     if os.environ.get("QB_ALL"):
         for rt in vpp.ResizeType:
             cfgs.append(("%s 256 rgb merged u8" % rt.name, vpp.FrameParameters(256, 256, resize_type=rt)))
