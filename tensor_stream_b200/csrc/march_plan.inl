@@ -318,46 +318,46 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
         return (int)(std::lower_bound(list.begin(), list.end(), row) - list.begin());
     };
     DeviceArena ar;
-    size_t off_row_l = 0, off_row_c = 0;
+    size_t off_row_l = 0, off_row_c = 0, off_gfl = 0, off_gfc = 0;
     int rows[64];
     if (bicubic) {
         std::vector<MarchRowB> rl((size_t)nstrips * R), rc((size_t)std::max(1, nstrips * (R / 2)));
         std::memset(rl.data(), 0, rl.size() * sizeof(MarchRowB));
         std::memset(rc.data(), 0, rc.size() * sizeof(MarchRowB));
+        std::vector<int> gfl((size_t)nstrips * G, 0), gfc((size_t)nstrips * G, 0);
         // `marched`: how far the window of the row's group has already been marched (-1 at the start of a group).
         // At the bottom border the reference pulls its taps back (yDiff = 0 when y+2 >= height, src/Resize.cu:36-39),
         // so a row's newest tap can lie BEHIND the previous row's: the window stays where it is and the taps are
-        // folded onto its bytes relative to the marched position.
+        // folded onto its bytes relative to the marched position (byte 0 = the marched slot).
         auto fill_row = [&](MarchRowB &r, const std::vector<int> &list, const int *srows, const double *cw, int q,
-                            bool lng, int &marched) -> bool {
+                            bool lng, int &marched, int *first_out) -> bool {
             int s[4];
             for (int k = 0; k < 4; ++k) s[k] = slot_of(list, srows[k]);
             const int oldest = std::min(std::min(s[0], s[1]), std::min(s[2], s[3]));
             marched = std::max(marched, std::max(std::max(s[0], s[1]), std::max(s[2], s[3])));
-            const int newest = marched;
-            if (newest - oldest > 3) return false;
-            long long m[4] = {0, 0, 0, 0};  // folded onto the window bytes: byte 3 = newest slot
+            if (marched - oldest > 3 || marched > 0xfff) return false;
+            long long m[4] = {0, 0, 0, 0};
             bool exact = true;
             unsigned tapsel = 0;
             for (int k = 0; k < 4; ++k) {
-                const int byte = 3 - (newest - s[k]);
+                const int byte = marched - s[k];
                 m[byte] += dyadic_m(cw[k], q, &exact);
                 tapsel |= (unsigned)byte << (4 * k);
             }
-            r.first = oldest;
-            r.newest = newest;
-            r.tapsel = tapsel;
-            r.exact = exact ? 1 : 0;
+            if (first_out) *first_out = oldest;
+            r.meta = (unsigned)marched | (tapsel << 12) | (exact ? 1u << 28 : 0u);
             return pack_digits(m, lng, r.w);
         };
         for (int st = 0; st < nstrips; ++st) {
             int last_valid = -1, marched = -1;
             for (int k = 0; k < R; ++k) {
                 const int i = st * R + k;
-                if (k % (2 * rpg) == 0) marched = -1;  // a new row group starts its own window
+                const bool gstart = k % (2 * rpg) == 0;
+                if (gstart) marched = -1;  // a new row group starts its own window
                 if (i < dh) {
                     luma_rows_of(i, rows);
-                    if (!fill_row(rl[i], SL.l[st], rows, in.cyw->data() + (size_t)4 * i, qy, ylong, marched))
+                    if (!fill_row(rl[i], SL.l[st], rows, in.cyw->data() + (size_t)4 * i, qy, ylong, marched,
+                                  gstart ? &gfl[(size_t)st * G + k / (2 * rpg)] : nullptr))
                         return TSVPP_UNSUPPORTED;
                     last_valid = i;
                 } else {
@@ -369,11 +369,13 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
                 marched = -1;
                 for (int k = 0; k < R / 2; ++k) {
                     const int ci = st * (R / 2) + k;
-                    if (k % rpg == 0) marched = -1;
+                    const bool gstart = k % rpg == 0;
+                    if (gstart) marched = -1;
                     if (ci < in.ch2) {
                         chroma_rows_of(ci, rows);
                         // vertical weights of chroma row ci are those of luma row index ci (src/Resize.cu:351-353)
-                        if (!fill_row(rc[ci], SL.c[st], rows, in.cyw->data() + (size_t)4 * std::min(ci, dh - 1), qy, ylong, marched))
+                        if (!fill_row(rc[ci], SL.c[st], rows, in.cyw->data() + (size_t)4 * std::min(ci, dh - 1), qy, ylong, marched,
+                                      gstart ? &gfc[(size_t)st * G + k / rpg] : nullptr))
                             return TSVPP_UNSUPPORTED;
                         last_valid = ci;
                     } else if (last_valid >= 0) {
@@ -384,6 +386,8 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
         }
         off_row_l = ar.add(rl.data(), rl.size() * sizeof(MarchRowB));
         off_row_c = ar.add(rc.data(), rc.size() * sizeof(MarchRowB));
+        off_gfl = ar.add(gfl.data(), gfl.size() * sizeof(int));
+        off_gfc = ar.add(gfc.data(), gfc.size() * sizeof(int));
     } else {
         std::vector<MarchRowA> rl((size_t)nstrips * R, MarchRowA{0, 0}), rc((size_t)std::max(1, nstrips * (R / 2)), MarchRowA{0, 0});
         for (int st = 0; st < nstrips; ++st) {
@@ -576,6 +580,7 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     D.nslots_l = (const int *)(base + off_nl); D.nslots_c = (const int *)(base + off_nc);
     D.col_l = base + off_col_l; D.col_c = base + off_col_c;
     D.row_l = base + off_row_l; D.row_c = base + off_row_c;
+    D.gfirst_l = (const int *)(base + off_gfl); D.gfirst_c = (const int *)(base + off_gfc);
     D.cxd = (const double *)(base + off_cxd); D.cyd = (const double *)(base + off_cyd);
     D.px_w = (const int *)(base + off_pxw); D.py_w = (const int *)(base + off_pyw);
     D.div_mul = (const unsigned *)(base + off_dmul); D.div_shift = (const int *)(base + off_dsh);

@@ -48,13 +48,14 @@ struct MarchColA {
     int prow;    // horizontal pattern row (j % PX), selects the weight words and, with the row's pattern row, the divisor
     int pad;
 };
-// bicubic: per output row (luma rows and chroma rows have separate tables)
+// bicubic: per output row (luma rows and chroma rows have separate tables).  Windows are kept newest-first:
+// byte 0 = the slot the group has marched to when this row is evaluated.
 struct MarchRowB {
-    int first;   // strip-relative slot of the oldest tap
-    int newest;  // strip-relative slot of the newest tap: slots up to here must have been marched
-    unsigned tapsel;  // PRMT selector that rebuilds the four taps (in tap order) from the window, for the FP64 tie path
-    int exact;
-    int w[4];    // vertical weight digits, folded onto the window bytes (byte 3 = slot `newest`)
+    unsigned meta;  // bits 0-11: strip-relative slot the window must have been marched to; bits 12-27: PRMT selector
+                    // that rebuilds the four taps (in tap order) from the window, for the FP64 tie path; bit 28: exact
+    int pad0;
+    int w[4];       // vertical weight digits folded onto the window bytes (w[0..1] sit in the first 16 bytes)
+    int pad1[2];
 };
 // area: per output row
 struct MarchRowA {
@@ -83,6 +84,7 @@ struct MarchPlanDev {
     const int *nslots_l, *nslots_c;                          // [nstrips]
     const void *col_l, *col_c;                               // [ntiles*tw] / [ntiles*tw/2]
     const void *row_l, *row_c;                               // [nstrips*R] / [nstrips*R/2]
+    const int *gfirst_l, *gfirst_c;                          // bicubic: [nstrips*G] slot of the oldest tap of a group's first row
     const double *cxd;                                       // bicubic: [dw][4] the reference's FP64 horizontal weights
     const double *cyd;                                       // bicubic: [dh][4] vertical ones (row i; chroma row ci uses row ci)
     const int *px_w;                                         // area: [PX][NW] packed u8 weights

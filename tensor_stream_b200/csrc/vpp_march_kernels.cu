@@ -37,9 +37,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
-// clamp(round_half_away(sum_k taps_k * m_k / 2^q), 0, 255) for integer weights m_k given as base-128
-// digits -- reference src/Resize.cu:49-51 (`int b = round(a0+a1+a2+a3); min 255; max 0`).  For s >= 0
-// round-half-away is floor(s + 1/2); negative sums clamp to 0 either way.
+// round_half_away(sum_k taps_k * m_k / 2^q) for integer weights m_k given as base-128 digits, NOT yet clamped
+// -- reference src/Resize.cu:49-51 (`int b = round(a0+a1+a2+a3); min 255; max 0`).  For s >= 0 round-half-away
+// is floor(s + 1/2); negative sums end up <= 0 and clamp to 0 either way.
 //   short (q <= 13): m = 128*w[1] + w[0], w[0] in [0,127], w[1] signed
 //   long  (15 <= q <= 27): m = 2^14 * (128*w[3] + w[2]) + (128*w[1] + w[0]), the low part in [0, 16383]:
 //         floor((hi*2^14 + lo + 2^(q-1)) / 2^q) = floor((hi + 2^(q-15) + floor(lo / 2^14)) / 2^(q-14))  (lo >= 0)
@@ -48,36 +48,43 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 // the FP64 sum by < 1e-12, which changes round() only where the exact sum is a tie -- every other multiple of
 // 2^-q is at least 2^-27 away from one.  Ties of inexact weights are re-evaluated with the reference's own
 // FP64 chain (bicubic_dot); everything else is exact by construction.
+struct QConst {  // per axis, in registers: short {q, 2^(q-1), 2^q - 1}; long {q-14, 2^(q-15), 2^(q-14) - 1}
+    int sh, half, mask;
+    __device__ __forceinline__ void set(int q, bool lng) {
+        sh = lng ? q - 14 : q;
+        half = lng ? (1 << (q - 15)) : (1 << (q - 1));
+        mask = (1 << sh) - 1;
+        asm volatile("" : "+r"(sh), "+r"(half), "+r"(mask));  // keep them out of the constant bank re-loads
+    }
+};
 template <bool LONG>
-__device__ __forceinline__ uint32_t idot_round_u8(uint32_t taps, const int (&w)[4], int q, bool &tie) {
-    int r;
+__device__ __forceinline__ int idot_raw(uint32_t taps, const int (&w)[4], const QConst &qc, bool &tie) {
     if constexpr (!LONG) {
-        const int lo = dp4a_us(taps, w[0], 1 << (q - 1));
+        const int lo = dp4a_us(taps, w[0], qc.half);
         const int hi = dp4a_us(taps, w[1], 0);
         const int t = hi * 128 + lo;
-        tie = (t & ((1 << q) - 1)) == 0;
-        r = t >> q;
+        tie = (t & qc.mask) == 0;
+        return t >> qc.sh;
     } else {
         const int lo = dp4a_us(taps, w[1], 0) * 128 + dp4a_us(taps, w[0], 0);
-        const int hi = dp4a_us(taps, w[3], 0) * 128 + dp4a_us(taps, w[2], 1 << (q - 15));
+        const int hi = dp4a_us(taps, w[3], 0) * 128 + dp4a_us(taps, w[2], qc.half);
         const int u = hi + (lo >> 14);
-        tie = ((lo & 16383) == 0) && ((u & ((1 << (q - 14)) - 1)) == 0);
-        r = u >> (q - 14);
+        tie = ((lo & 16383) == 0) && ((u & qc.mask) == 0);
+        return u >> qc.sh;
     }
-    return (uint32_t)min(max(r, 0), 255);
+}
+__device__ __forceinline__ uint32_t clamp_u8(int r) { return (uint32_t)min(max(r, 0), 255); }
+// (c << 16) | (sat_u8(a) << 8) | sat_u8(b): two saturating conversions and a two-byte shift of `c` in ONE
+// instruction (SASS I2IP.U8.S32.SAT) -- marches a window by two slots: a = older, b = newest
+__device__ __forceinline__ uint32_t pack_sat2(int a, int b, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 // the tie path: reference src/Resize.cu:45-51 with its FP64 weights (taps in tap order, one per byte)
-__device__ __noinline__ uint32_t bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps) {
-    return (uint32_t)bicubic_dot(c[0], c[1], c[2], c[3], (int)(taps & 0xffu), (int)((taps >> 8) & 0xffu),
-                                 (int)((taps >> 16) & 0xffu), (int)(taps >> 24));
-}
-template <bool LONG>
-__device__ __forceinline__ uint32_t bicubic_sum_u8(uint32_t taps, const int (&w)[4], int q, int exact,
-                                                   const double *__restrict__ cd) {
-    bool tie;
-    uint32_t r = idot_round_u8<LONG>(taps, w, q, tie);
-    if (tie && !exact) r = bicubic_tie_fp64(cd, taps);
-    return r;
+__device__ __forceinline__ int bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps) {
+    return bicubic_dot(__ldg(c), __ldg(c + 1), __ldg(c + 2), __ldg(c + 3), (int)(taps & 0xffu), (int)((taps >> 8) & 0xffu),
+                       (int)((taps >> 16) & 0xffu), (int)(taps >> 24));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -144,30 +151,193 @@ struct BicubicCols {
     // two luma columns and one chroma pair
     int addr0, addr1, addrc;
     uint32_t sel0, sel1, selcA, selcB;
-    int ex0, ex1, exc;  // weights exactly dyadic (no FP64 tie path)
+    int inexact;  // bit 0 / 1 / 2: the weights of column 0 / column 1 / the chroma pair are only NEAR dyadic (FP64 tie path)
     int w0[4], w1[4], wc[4];
     __device__ __forceinline__ void load(const MarchColB *cl, const MarchColB *cc) {
         const int4 a0 = __ldg(reinterpret_cast<const int4 *>(cl));
         const int4 b0 = __ldg(reinterpret_cast<const int4 *>(cl) + 1);
         const int4 a1 = __ldg(reinterpret_cast<const int4 *>(cl + 1));
         const int4 b1 = __ldg(reinterpret_cast<const int4 *>(cl + 1) + 1);
-        addr0 = a0.x; sel0 = (uint32_t)a0.y; ex0 = a0.w;
-        addr1 = a1.x; sel1 = (uint32_t)a1.y; ex1 = a1.w;
+        addr0 = a0.x; sel0 = (uint32_t)a0.y;
+        addr1 = a1.x; sel1 = (uint32_t)a1.y;
+        inexact = (a0.w ? 0 : 1) | (a1.w ? 0 : 2);
         w0[0] = b0.x; w0[1] = b0.y; w0[2] = b0.z; w0[3] = b0.w;
         w1[0] = b1.x; w1[1] = b1.y; w1[2] = b1.z; w1[3] = b1.w;
         if (cc) {
             const int4 ac = __ldg(reinterpret_cast<const int4 *>(cc));
             const int4 bc = __ldg(reinterpret_cast<const int4 *>(cc) + 1);
-            addrc = ac.x; selcA = (uint32_t)ac.y; selcB = (uint32_t)ac.z; exc = ac.w;
+            addrc = ac.x; selcA = (uint32_t)ac.y; selcB = (uint32_t)ac.z;
+            inexact |= ac.w ? 0 : 4;
             wc[0] = bc.x; wc[1] = bc.y; wc[2] = bc.z; wc[3] = bc.w;
         }
     }
 };
 
 // ---------------------------------------------------------------------------------------
+// bicubic: one thread, two output columns, the rpg row pairs of its row group
+// ---------------------------------------------------------------------------------------
+// Windows hold the horizontal sums of the last four marched slots, byte 0 = newest.  A march of two slots is
+// one I2IP (pack_sat2), of one slot a clamp + PRMT; the FP64 tie path patches the raw sums before they are packed.
+template <bool XL, bool YL, int OK, bool NEED_UV>
+__device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const BicubicCols<XL> &bc, uint32_t stage,
+                                                    uint32_t stage_c, uint32_t sstride, int strip, int g, int j0,
+                                                    bool have_c, bool vec, void *outp) {
+    const int R2 = P.G * P.rpg;
+    const int pr0 = strip * R2 + g * P.rpg;  // first row pair (global index) of this thread's group
+    const MarchRowB *rowl = reinterpret_cast<const MarchRowB *>(P.row_l);
+    const MarchRowB *rowc = reinterpret_cast<const MarchRowB *>(P.row_c);
+    const double *cxd = P.cxd, *cyd = P.cyd;
+    QConst qx, qy;
+    qx.set(P.qx, XL);
+    qy.set(P.qy, YL);
+    const int dh = P.e.dh, ch2 = P.e.ch2, rpg = P.rpg;
+
+    // one march step of the two luma columns over `n` (1 or 2) slots starting at shared address sl
+    auto luma_step2 = [&](uint32_t sl, uint32_t &W0, uint32_t &W1) {
+        const uint32_t a0 = lds32(sl + bc.addr0), a1 = lds32(sl + bc.addr0 + 4);
+        const uint32_t b0 = lds32(sl + bc.addr1), b1 = lds32(sl + bc.addr1 + 4);
+        const uint32_t c0 = lds32(sl + sstride + bc.addr0), c1 = lds32(sl + sstride + bc.addr0 + 4);
+        const uint32_t d0 = lds32(sl + sstride + bc.addr1), d1 = lds32(sl + sstride + bc.addr1 + 4);
+        const uint32_t tA0 = __byte_perm(a0, a1, bc.sel0), tA1 = __byte_perm(b0, b1, bc.sel1);
+        const uint32_t tB0 = __byte_perm(c0, c1, bc.sel0), tB1 = __byte_perm(d0, d1, bc.sel1);
+        bool zA0, zA1, zB0, zB1;
+        int rA0 = idot_raw<XL>(tA0, bc.w0, qx, zA0), rA1 = idot_raw<XL>(tA1, bc.w1, qx, zA1);
+        int rB0 = idot_raw<XL>(tB0, bc.w0, qx, zB0), rB1 = idot_raw<XL>(tB1, bc.w1, qx, zB1);
+        if ((((zA0 | zB0) ? 1 : 0) | ((zA1 | zB1) ? 2 : 0)) & bc.inexact) {
+            if (zA0 && (bc.inexact & 1)) rA0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tA0);
+            if (zB0 && (bc.inexact & 1)) rB0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tB0);
+            if (zA1 && (bc.inexact & 2)) rA1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tA1);
+            if (zB1 && (bc.inexact & 2)) rB1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tB1);
+        }
+        W0 = pack_sat2(rA0, rB0, W0);
+        W1 = pack_sat2(rA1, rB1, W1);
+    };
+    auto luma_step1 = [&](uint32_t sl, uint32_t &W0, uint32_t &W1) {
+        const uint32_t a0 = lds32(sl + bc.addr0), a1 = lds32(sl + bc.addr0 + 4);
+        const uint32_t b0 = lds32(sl + bc.addr1), b1 = lds32(sl + bc.addr1 + 4);
+        const uint32_t tA0 = __byte_perm(a0, a1, bc.sel0), tA1 = __byte_perm(b0, b1, bc.sel1);
+        bool zA0, zA1;
+        int rA0 = idot_raw<XL>(tA0, bc.w0, qx, zA0), rA1 = idot_raw<XL>(tA1, bc.w1, qx, zA1);
+        if (((zA0 ? 1 : 0) | (zA1 ? 2 : 0)) & bc.inexact) {
+            if (zA0 && (bc.inexact & 1)) rA0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tA0);
+            if (zA1 && (bc.inexact & 2)) rA1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tA1);
+        }
+        W0 = __byte_perm(W0, clamp_u8(rA0), 0x2104);  // (W << 8) | new
+        W1 = __byte_perm(W1, clamp_u8(rA1), 0x2104);
+    };
+    // chroma pair cj = j0/2 uses the horizontal weights of luma column cj (src/Resize.cu:351-353)
+    auto chroma_taps = [&](uint32_t sl, uint32_t &tu, uint32_t &tv) {
+        const uint32_t x0 = lds32(sl), x1 = lds32(sl + 4), x2 = lds32(sl + 8);
+        tu = __byte_perm(__byte_perm(x0, x1, bc.selcA & 0xffffu), x2, bc.selcB & 0xffffu);
+        tv = __byte_perm(__byte_perm(x0, x1, bc.selcA >> 16), x2, bc.selcB >> 16);
+    };
+    auto chroma_step2 = [&](uint32_t sl, uint32_t &WU, uint32_t &WV) {
+        uint32_t uA, vA, uB, vB;
+        chroma_taps(sl, uA, vA);
+        chroma_taps(sl + sstride, uB, vB);
+        bool z0, z1, z2, z3;
+        int rUA = idot_raw<XL>(uA, bc.wc, qx, z0), rVA = idot_raw<XL>(vA, bc.wc, qx, z1);
+        int rUB = idot_raw<XL>(uB, bc.wc, qx, z2), rVB = idot_raw<XL>(vB, bc.wc, qx, z3);
+        if ((z0 | z1 | z2 | z3) && (bc.inexact & 4)) {
+            const double *cd = cxd + 4 * (size_t)(j0 >> 1);
+            if (z0) rUA = bicubic_tie_fp64(cd, uA);
+            if (z1) rVA = bicubic_tie_fp64(cd, vA);
+            if (z2) rUB = bicubic_tie_fp64(cd, uB);
+            if (z3) rVB = bicubic_tie_fp64(cd, vB);
+        }
+        WU = pack_sat2(rUA, rUB, WU);
+        WV = pack_sat2(rVA, rVB, WV);
+    };
+    auto chroma_step1 = [&](uint32_t sl, uint32_t &WU, uint32_t &WV) {
+        uint32_t uA, vA;
+        chroma_taps(sl, uA, vA);
+        bool z0, z1;
+        int rUA = idot_raw<XL>(uA, bc.wc, qx, z0), rVA = idot_raw<XL>(vA, bc.wc, qx, z1);
+        if ((z0 | z1) && (bc.inexact & 4)) {
+            const double *cd = cxd + 4 * (size_t)(j0 >> 1);
+            if (z0) rUA = bicubic_tie_fp64(cd, uA);
+            if (z1) rVA = bicubic_tie_fp64(cd, vA);
+        }
+        WU = __byte_perm(WU, clamp_u8(rUA), 0x2104);
+        WV = __byte_perm(WV, clamp_u8(rVA), 0x2104);
+    };
+    // row records: first 16 bytes {meta, -, w0, w1}, next 16 {w2, w3, -, -} (read for long vertical digits only)
+    auto load_row = [&](const MarchRowB *r, int4 &lo, int4 &hi) {
+        lo = __ldg(reinterpret_cast<const int4 *>(r));
+        if (YL) hi = __ldg(reinterpret_cast<const int4 *>(r) + 1);
+    };
+    // vertical sums of two windows that share a row record; tie path with the row's FP64 weights
+    auto vsum2 = [&](uint32_t Wa, uint32_t Wb, const int4 &lo, const int4 &hi, const double *cd, int &ra, int &rb) {
+        const int wv[4] = {lo.z, lo.w, YL ? hi.x : 0, YL ? hi.y : 0};
+        bool za, zb;
+        ra = idot_raw<YL>(Wa, wv, qy, za);
+        rb = idot_raw<YL>(Wb, wv, qy, zb);
+        const uint32_t meta = (uint32_t)lo.x;
+        if ((za | zb) && !(meta >> 28)) {
+            const uint32_t tapsel = (meta >> 12) & 0xffffu;  // window bytes back into tap order
+            if (za) ra = bicubic_tie_fp64(cd, __byte_perm(Wa, 0u, tapsel));
+            if (zb) rb = bicubic_tie_fp64(cd, __byte_perm(Wb, 0u, tapsel));
+        }
+        ra = (int)clamp_u8(ra);
+        rb = (int)clamp_u8(rb);
+    };
+
+    uint32_t WY0 = 0, WY1 = 0, WU = 0, WV = 0;
+    int curl = __ldg(P.gfirst_l + strip * P.G + g) - 1;
+    int curc = NEED_UV ? __ldg(P.gfirst_c + strip * P.G + g) - 1 : 0;
+    uint32_t sl_l = stage + (uint32_t)(curl + 1) * sstride;    // shared address of the next luma slot to march
+    uint32_t sl_c = stage_c + (uint32_t)(curc + 1) * sstride + (uint32_t)bc.addrc;
+    int4 ra_lo, ra_hi = make_int4(0, 0, 0, 0);
+    load_row(rowl + 2 * pr0, ra_lo, ra_hi);
+    for (int p = 0; p < rpg; ++p) {
+        const int pr = pr0 + p;
+        const int i0 = 2 * pr;
+        if (i0 >= dh) break;  // uniform: rows past the image
+        // the records of this pair's second row and chroma row are requested before the first row's work
+        int4 rb_lo, rb_hi = make_int4(0, 0, 0, 0), rc_lo = make_int4(0, 0, 0, 0), rc_hi = make_int4(0, 0, 0, 0);
+        load_row(rowl + i0 + 1, rb_lo, rb_hi);
+        if (NEED_UV) load_row(rowc + pr, rc_lo, rc_hi);
+        int Yv[2][2];
+        int UV[1][2] = {{0, 0}};
+        {
+            int n = (int)((uint32_t)ra_lo.x & 0xfffu) - curl;  // uniform
+            curl += n;
+            for (; n >= 2; n -= 2, sl_l += 2 * sstride) luma_step2(sl_l, WY0, WY1);
+            if (n > 0) { luma_step1(sl_l, WY0, WY1); sl_l += sstride; }
+            vsum2(WY0, WY1, ra_lo, ra_hi, cyd + 4 * (size_t)i0, Yv[0][0], Yv[0][1]);
+        }
+        if (p + 1 < rpg) load_row(rowl + i0 + 2, ra_lo, ra_hi);  // next pair's first row
+        {
+            int n = (int)((uint32_t)rb_lo.x & 0xfffu) - curl;
+            curl += n;
+            for (; n >= 2; n -= 2, sl_l += 2 * sstride) luma_step2(sl_l, WY0, WY1);
+            if (n > 0) { luma_step1(sl_l, WY0, WY1); sl_l += sstride; }
+            vsum2(WY0, WY1, rb_lo, rb_hi, cyd + 4 * (size_t)(i0 + 1), Yv[1][0], Yv[1][1]);
+        }
+        if (NEED_UV && pr < ch2) {
+            int n = (int)((uint32_t)rc_lo.x & 0xfffu) - curc;
+            curc += n;
+            for (; n >= 2; n -= 2, sl_c += 2 * sstride) chroma_step2(sl_c, WU, WV);
+            if (n > 0) { chroma_step1(sl_c, WU, WV); sl_c += sstride; }
+            int u, v;
+            vsum2(WU, WV, rc_lo, rc_hi, cyd + 4 * (size_t)pr, u, v);
+            if (have_c) { UV[0][0] = u; UV[0][1] = v; }
+        }
+        const int nx = min(2, P.e.dw - j0), ny = min(2, dh - i0);
+        if (nx > 0) {
+            if (nx == 2 && ny == 2 && vec)
+                emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, 2, 2, true);
+            else
+                emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-// MODE: MARCH_BICUBIC / MARCH_AREA.  VAR: bicubic: XLONG (0/1); area: NW (1, 2 or 4).
+// MODE: MARCH_BICUBIC / MARCH_AREA.  VAR: bicubic: bit 0 = long horizontal digits, bit 1 = long vertical digits;
+// area: NW (1, 2 or 4).
 template <int MODE, int VAR, int OK>
 __global__ void __launch_bounds__(kMarchMaxThreads, 2)
     vpp_march_kernel(const MarchPlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
@@ -224,7 +394,7 @@ __global__ void __launch_bounds__(kMarchMaxThreads, 2)
 
     int cur_tile = -1;
     // per-tile column state
-    BicubicCols<(MODE == MARCH_BICUBIC) && (VAR != 0)> bc;
+    BicubicCols<(MODE == MARCH_BICUBIC) && ((VAR & 1) != 0)> bc;
     int a_addr0 = 0, a_addr1 = 0, a_addrc = 0, a_sh0 = 0, a_sh1 = 0, a_shc = 0, a_pr0 = 0, a_pr1 = 0, a_prc = 0;
     constexpr int NW = (MODE == MARCH_AREA) ? VAR : 1;
     uint32_t a_w0[NW], a_w1[NW], a_wc[NW];
@@ -268,83 +438,16 @@ __global__ void __launch_bounds__(kMarchMaxThreads, 2)
         mbar_wait(full + s, phase);
 
         if (active) {
-            const int pr0 = ic.strip * R2 + g * P.rpg;  // first row pair (global index) of this thread's group
             void *outp = frames[ic.frame].out;
             if constexpr (MODE == MARCH_BICUBIC) {
-                constexpr bool XL = VAR != 0;
-                const MarchRowB *rowl = reinterpret_cast<const MarchRowB *>(P.row_l);
-                const MarchRowB *rowc = reinterpret_cast<const MarchRowB *>(P.row_c);
-                const double *cxd = P.cxd, *cyd = P.cyd;
-                const int qy = P.qy, ylong = P.ylong;
-                // vertical sum of a window; `tapsel` puts the window bytes back into tap order for the tie path
-                auto vsum = [&](uint32_t Wn, const int (&wv)[4], uint32_t tapsel, int exact, const double *cd) -> uint32_t {
-                    bool tie;
-                    uint32_t r = ylong ? idot_round_u8<true>(Wn, wv, qy, tie) : idot_round_u8<false>(Wn, wv, qy, tie);
-                    if (tie && !exact) r = bicubic_tie_fp64(cd, __byte_perm(Wn, 0u, tapsel));
-                    return r;
-                };
-                // windows of the last four marched slots: byte 3 = newest
-                uint32_t WY0 = 0, WY1 = 0, WU = 0, WV = 0;
-                int curl = __ldg(&rowl[2 * pr0].first) - 1;
-                int curc = NEED_UV ? __ldg(&rowc[pr0].first) - 1 : 0;
-                for (int p = 0; p < P.rpg; ++p) {
-                    const int pr = pr0 + p;
-                    const int i0 = 2 * pr;
-                    if (i0 >= P.e.dh) break;  // uniform: rows past the image
-                    int Yv[2][2];
-                    int UV[1][2] = {{0, 0}};
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        const int4 r0 = __ldg(reinterpret_cast<const int4 *>(rowl + i0 + a));
-                        const int4 r1 = __ldg(reinterpret_cast<const int4 *>(rowl + i0 + a) + 1);
-                        const int newest = r0.y;
-                        const int wv[4] = {r1.x, r1.y, r1.z, r1.w};
-                        while (curl < newest) {  // uniform trip count
-                            ++curl;
-                            const uint32_t sl = stage + (uint32_t)curl * sstride;
-                            const uint32_t t0 = __byte_perm(lds32(sl + bc.addr0), lds32(sl + bc.addr0 + 4), bc.sel0);
-                            const uint32_t t1 = __byte_perm(lds32(sl + bc.addr1), lds32(sl + bc.addr1 + 4), bc.sel1);
-                            const uint32_t h0 = bicubic_sum_u8<XL>(t0, bc.w0, P.qx, bc.ex0, cxd + 4 * (size_t)j0);
-                            const uint32_t h1 = bicubic_sum_u8<XL>(t1, bc.w1, P.qx, bc.ex1, cxd + 4 * (size_t)(j0 + 1));
-                            WY0 = __byte_perm(WY0, h0, 0x4321);
-                            WY1 = __byte_perm(WY1, h1, 0x4321);
-                        }
-                        Yv[a][0] = (int)vsum(WY0, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)(i0 + a));
-                        Yv[a][1] = (int)vsum(WY1, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)(i0 + a));
-                    }
-                    if (NEED_UV && pr < P.e.ch2) {
-                        const int4 r0 = __ldg(reinterpret_cast<const int4 *>(rowc + pr));
-                        const int4 r1 = __ldg(reinterpret_cast<const int4 *>(rowc + pr) + 1);
-                        const int newest = r0.y;
-                        const int wv[4] = {r1.x, r1.y, r1.z, r1.w};
-                        while (curc < newest) {
-                            ++curc;
-                            const uint32_t sl = stage_c + (uint32_t)curc * sstride + (uint32_t)bc.addrc;
-                            const uint32_t x0 = lds32(sl), x1 = lds32(sl + 4), x2 = lds32(sl + 8);
-                            const uint32_t tu = __byte_perm(__byte_perm(x0, x1, bc.selcA & 0xffffu), x2, bc.selcB & 0xffffu);
-                            const uint32_t tv = __byte_perm(__byte_perm(x0, x1, bc.selcA >> 16), x2, bc.selcB >> 16);
-                            // chroma pair cj = j0/2 uses the horizontal weights of luma column cj (src/Resize.cu:351-353)
-                            WU = __byte_perm(WU, bicubic_sum_u8<XL>(tu, bc.wc, P.qx, bc.exc, cxd + 4 * (size_t)(j0 >> 1)), 0x4321);
-                            WV = __byte_perm(WV, bicubic_sum_u8<XL>(tv, bc.wc, P.qx, bc.exc, cxd + 4 * (size_t)(j0 >> 1)), 0x4321);
-                        }
-                        if (have_c) {
-                            UV[0][0] = (int)vsum(WU, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)pr);
-                            UV[0][1] = (int)vsum(WV, wv, (uint32_t)r0.z, r0.w, cyd + 4 * (size_t)pr);
-                        }
-                    }
-                    const int nx = min(2, P.e.dw - j0), ny = min(2, P.e.dh - i0);
-                    if (nx > 0) {
-                        if (nx == 2 && ny == 2 && vec)
-                            emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, 2, 2, true);
-                        else
-                            emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
-                    }
-                }
+                march_bicubic_group<(VAR & 1) != 0, (VAR & 2) != 0, OK, NEED_UV>(P, bc, stage, stage_c, sstride, ic.strip, g, j0,
+                                                                                  have_c, vec, outp);
             } else {
                 // ---- area ----
                 const MarchRowA *rowl = reinterpret_cast<const MarchRowA *>(P.row_l);
                 const MarchRowA *rowc = reinterpret_cast<const MarchRowA *>(P.row_c);
                 const int K = P.K;
+                const int pr0 = ic.strip * R2 + g * P.rpg;  // first row pair (global index) of this thread's group
                 for (int p = 0; p < P.rpg; ++p) {
                     const int pr = pr0 + p;
                     const int i0 = 2 * pr;
@@ -446,7 +549,14 @@ static MarchFn pick_ok(int ok) {
     return nullptr;
 }
 static MarchFn pick_march(const MarchPlanDev &P, int ok) {
-    if (P.mode == MARCH_BICUBIC) return P.xlong ? pick_ok<MARCH_BICUBIC, 1>(ok) : pick_ok<MARCH_BICUBIC, 0>(ok);
+    if (P.mode == MARCH_BICUBIC) {
+        switch ((P.xlong ? 1 : 0) | (P.ylong ? 2 : 0)) {
+            case 0: return pick_ok<MARCH_BICUBIC, 0>(ok);
+            case 1: return pick_ok<MARCH_BICUBIC, 1>(ok);
+            case 2: return pick_ok<MARCH_BICUBIC, 2>(ok);
+            default: return pick_ok<MARCH_BICUBIC, 3>(ok);
+        }
+    }
     switch (P.NW) {
         case 1: return pick_ok<MARCH_AREA, 1>(ok);
         case 2: return pick_ok<MARCH_AREA, 2>(ok);
