@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <memory>
 #include <mutex>
@@ -72,6 +73,25 @@ int colorConversionKernel(AVFrame *src, AVFrame *dst, ColorOptions color, int ma
 int resizeKernel(AVFrame *src, AVFrame *dst, bool crop, ResizeOptions resize, int maxThreadsPerBlock, cudaStream_t *stream);
 int cropHost(AVFrame *src, AVFrame *dst, CropOptions crop, int maxThreadsPerBlock, cudaStream_t *stream);
 
+// Which AVFrame does the code that INCLUDES this header see?  libtsvpp.so is compiled against either FFmpeg's
+// <libavutil/frame.h> or, where no FFmpeg headers exist, the minimal struct of tsvpp_avframe.h; the two lay
+// `width`, `height` and `opaque` out differently.  Every translation unit that includes this header reports its own
+// layout when the program starts; after a mismatch VideoProcessor::Init refuses to run (VREADER_ERROR) instead of
+// writing output->opaque at the wrong offset.  Rebuild the library with the same headers as the caller
+// (python -m tensor_stream_b200.build, TSVPP_FFMPEG_INCLUDE=<dir>), see INTEGRATION.md.
+extern "C" int tsvpp_vp_register_avframe_layout(size_t off_linesize, size_t off_width, size_t off_height, size_t off_opaque,
+                                                size_t size);
+extern "C" const char *tsvpp_vp_avframe_flavour(void);  // "ffmpeg" or "shim": what the library was built against
+namespace tsvpp_detail {
+struct AvFrameLayoutCheck {
+    AvFrameLayoutCheck() {
+        tsvpp_vp_register_avframe_layout(offsetof(AVFrame, linesize), offsetof(AVFrame, width), offsetof(AVFrame, height),
+                                         offsetof(AVFrame, opaque), sizeof(AVFrame));
+    }
+};
+static AvFrameLayoutCheck avframe_layout_check_instance;
+}  // namespace tsvpp_detail
+
 class VideoProcessor {
 public:
     int Init(std::shared_ptr<Logger> logger, uint8_t maxConsumers = 5, bool _enableDumps = false);
@@ -93,4 +113,8 @@ private:
     std::mutex dumpSync;
     bool isClosed = true;
     std::shared_ptr<Logger> logger;
+    // Frames of consumers that call Convert at the same time are converted by one fused launch
+    // (tsvpp_convert_coalesced); TSVPP_COALESCE=0 at Init keeps one launch per call on the consumer's own stream.
+    bool coalesce = true;
+    cudaStream_t coStream = nullptr;
 };

@@ -92,6 +92,18 @@ int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const
 int tsvpp_batch_run(TsvppBatch *batch, void *stream);
 void tsvpp_batch_destroy(TsvppBatch *batch);
 
+/* Per-frame entry for pipelines that call once per decoded frame from several consumer threads (the reference's
+ * TensorStream::getFrame -> VideoProcessor::Convert, src/Wrappers/WrapperPython.cpp:265-350): calls that are pending
+ * at the same time and agree on geometry and parameters are converted by ONE fused launch on the context's
+ * coalescing stream.  `out` must be usable on that stream (e.g. cudaMallocAsync'd on tsvpp_coalesce_stream()).
+ * wait != 0: return when this frame's result is complete; wait == 0: return once the launch that covers it has been
+ * issued (stream-ordered; the coalescing stream is a blocking stream, so work on the legacy default stream is
+ * ordered after it like after the reference's per-consumer streams). */
+int tsvpp_convert_coalesced(TsvppContext *ctx, const TsvppFrame *frame, const TsvppParams *p, void *out, int wait);
+void *tsvpp_coalesce_stream(TsvppContext *ctx);
+/* frames converted / launches issued by tsvpp_convert_coalesced so far (their ratio is the mean batch size) */
+int tsvpp_coalesce_stats(const TsvppContext *ctx, unsigned long long *frames, unsigned long long *launches);
+
 /* End-to-end entry with HOST buffers: each frame is a host NV12 image (y: height*pitch_y bytes,
  * uv: height/2*pitch_uv bytes); outputs are written to host memory.  Copies are pipelined with
  * the kernel over internal streams; returns when all outputs are complete.  `frames[i].y/uv` and
@@ -109,6 +121,8 @@ unsigned long long tsvpp_launch_count(const TsvppContext *ctx);
 /* Human-readable description of the plan chosen for (geometry, params): tile width, stages,
  * smem bytes, fill mode ("bulk" = cp.async.bulk/TMA, "ldg" = fallback for unaligned frames). */
 int tsvpp_describe_plan(TsvppContext *ctx, const TsvppFrame *frame0, const TsvppParams *p, char *buf, size_t buflen);
+/* number of plans currently cached by the context (LRU-bounded, TSVPP_MAX_PLANS, default 64) */
+int tsvpp_plan_cache_size(TsvppContext *ctx);
 
 /* Test hook: pow(w,2) and pow(w,3) as evaluated by the device's libdevice (the bicubic weights of
  * reference src/Resize.cu:45-48 depend on it bit for bit; the CPU oracle is pinned to these). */

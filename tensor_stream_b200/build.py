@@ -31,7 +31,11 @@ def _stale(target, deps):
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defs=(), out=None):
+    """defs / out: developer A/B builds (extra -D flags into another .so, see tools/ab_build.sh)."""
+    global LIB
+    if out:
+        LIB, force = out, True
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     if not force and not _stale(LIB, deps):
@@ -39,7 +43,9 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for s in srcs:  # the translation units compile in parallel
         o = os.path.join(CSRC, os.path.basename(s) + ".o")
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        if out:
+            o = os.path.join("/tmp", os.path.basename(out) + "." + os.path.basename(s) + ".o")
+        cmd = ["nvcc"] + NVCC_FLAGS + list(defs) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         if s.endswith(".cpp"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")
@@ -55,4 +61,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    _out = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defs=_defs, out=_out[0] if _out else None))

@@ -10,12 +10,70 @@
 // intermediates in HBM and the per-frame AREA pattern upload.
 #include "VideoProcessor.h"
 
+#include <nvtx3/nvToolsExt.h>
+
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
+#include <iostream>
 #include <map>
 #include <mutex>
+#include <thread>
 
 #include "tsvpp.h"
+
+// NVTX ranges with the reference's names and colour (include/Common.h:72-105 PUSH_RANGE; pushed at
+// src/VideoProcessor.cpp:51,80,95) when the Logger asks for them.
+namespace {
+class NVTXTracer {
+public:
+    void trace(const char *name, uint32_t argb) {
+        nvtxEventAttributes_t a = {};
+        a.version = NVTX_VERSION;
+        a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+        a.colorType = NVTX_COLOR_ARGB;
+        a.color = argb;
+        a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+        a.message.ascii = name;
+        nvtxRangePushEx(&a);
+        pushed = true;
+    }
+    ~NVTXTracer() {
+        if (pushed) nvtxRangePop();
+    }
+
+private:
+    bool pushed = false;
+};
+constexpr uint32_t kNvtxYellow = 0xffffff00u;  // NVTXColors::YELLOW
+}  // namespace
+#define PUSH_RANGE(name, colorID)             \
+    NVTXTracer tracer;                        \
+    if (logger && logger->enableNVTX) {       \
+        tracer.trace(name, colorID);          \
+    }
+
+// ---------------------------------------------------------------------------------------------
+// AVFrame layout agreement between this library and its callers (see include/VideoProcessor.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+std::atomic<int> g_avframe_mismatch{0};
+}
+extern "C" const char *tsvpp_vp_avframe_flavour(void) { return TSVPP_AVFRAME_FLAVOUR; }
+extern "C" int tsvpp_vp_register_avframe_layout(size_t off_linesize, size_t off_width, size_t off_height, size_t off_opaque,
+                                                size_t size) {
+    const bool same = off_linesize == offsetof(AVFrame, linesize) && off_width == offsetof(AVFrame, width) &&
+                      off_height == offsetof(AVFrame, height) && off_opaque == offsetof(AVFrame, opaque) &&
+                      size == sizeof(AVFrame);
+    if (!same) {
+        g_avframe_mismatch.store(1);
+        std::cout << "libtsvpp: AVFrame layout mismatch: the library was built against the '" << TSVPP_AVFRAME_FLAVOUR
+                  << "' AVFrame (opaque at " << offsetof(AVFrame, opaque) << ", size " << sizeof(AVFrame)
+                  << "), the caller has opaque at " << off_opaque << ", size " << size
+                  << "; rebuild libtsvpp.so with the caller's headers\n" << std::flush;
+    }
+    return same ? 0 : -1;
+}
 
 float channelsByFourCC(FourCC fourCC) {
     switch (fourCC) {
@@ -217,6 +275,8 @@ template int colorConversionKernel<float>(AVFrame *, AVFrame *, ColorOptions, in
 int VideoProcessor::Init(std::shared_ptr<Logger> lg, uint8_t maxConsumers, bool _enableDumps) {
     enableDumps = _enableDumps;
     logger = lg;
+    PUSH_RANGE("VideoProcessor::Init", kNvtxYellow);
+    if (g_avframe_mismatch.load()) return VREADER_ERROR;  // see tsvpp_vp_register_avframe_layout
     // the reference always queried device 0 (src/VideoProcessor.cpp:83); use the current one
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return (int)e;
@@ -237,11 +297,20 @@ int VideoProcessor::Init(std::shared_ptr<Logger> lg, uint8_t maxConsumers, bool 
         if (e != cudaSuccess) return (int)e;
         streamArr.push_back(std::make_pair(std::string("empty"), s));
     }
+    {
+        const char *e = std::getenv("TSVPP_COALESCE");
+        coalesce = !(e && *e == '0');
+        if (coalesce) {
+            coStream = (cudaStream_t)tsvpp_coalesce_stream(ctx);
+            if (!coStream) return VREADER_ERROR;
+        }
+    }
     isClosed = false;
     return VREADER_OK;
 }
 
 int VideoProcessor::Convert(AVFrame *input, AVFrame *output, FrameParameters &options, std::string consumerName) {
+    PUSH_RANGE("VideoProcessor::Convert", kNvtxYellow);
     if (isClosed || !ctx) return VREADER_ERROR;
     cudaStream_t stream;
     {
@@ -261,14 +330,37 @@ int VideoProcessor::Convert(AVFrame *input, AVFrame *output, FrameParameters &op
     size_t elems = 0;
     int rc = tsvpp_output_info(f.width, f.height, &p, &ow, &oh, &elems, &es);
     if (rc) return rc;
+    // The reference's Convert returns with the work complete in every resize/crop path (its
+    // cudaFree calls synchronise the device).  Keep that guarantee unless the caller opts out.
+    static const bool async_mode = [] {
+        const char *s = std::getenv("TSVPP_ASYNC");
+        return s && *s == '1';
+    }();
     void *dst = nullptr;
-    cudaError_t e = cudaMallocAsync(&dst, elems * (size_t)es, stream);
-    if (e != cudaSuccess) return (int)e;
-    void *outs[1] = {dst};
-    rc = tsvpp_convert_batch(ctx, &f, 1, &p, outs, stream);
-    if (rc) {
-        cudaFreeAsync(dst, stream);
-        return rc;
+    cudaError_t e;
+    if (coalesce) {
+        // the result buffer is allocated on the coalescing stream by the caller's own thread (stream-ordered, no
+        // lock of ours), then the frame joins whatever launch is being assembled
+        e = cudaMallocAsync(&dst, elems * (size_t)es, coStream);
+        if (e != cudaSuccess) return (int)e;
+        rc = tsvpp_convert_coalesced(ctx, &f, &p, dst, async_mode ? 0 : 1);
+        if (rc) {
+            cudaFreeAsync(dst, coStream);
+            return rc;
+        }
+    } else {
+        e = cudaMallocAsync(&dst, elems * (size_t)es, stream);
+        if (e != cudaSuccess) return (int)e;
+        void *outs[1] = {dst};
+        rc = tsvpp_convert_batch(ctx, &f, 1, &p, outs, stream);
+        if (rc) {
+            cudaFreeAsync(dst, stream);
+            return rc;
+        }
+        if (!async_mode) {
+            e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     output->opaque = dst;
     output->width = ow;
@@ -277,16 +369,6 @@ int VideoProcessor::Convert(AVFrame *input, AVFrame *output, FrameParameters &op
     if (options.resize.width == 0 || options.resize.height == 0) {  // reference :132-135
         options.resize.width = (unsigned)ow;
         options.resize.height = (unsigned)oh;
-    }
-    // The reference's Convert returns with the work complete in every resize/crop path (its
-    // cudaFree calls synchronise the device).  Keep that guarantee unless the caller opts out.
-    static const bool async_mode = [] {
-        const char *s = std::getenv("TSVPP_ASYNC");
-        return s && *s == '1';
-    }();
-    if (!async_mode) {
-        e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) return (int)e;
     }
     if (enableDumps) {
         const std::string fileName = std::string("Processed_") + consumerName + std::string(".yuv");
@@ -303,6 +385,7 @@ int VideoProcessor::Convert(AVFrame *input, AVFrame *output, FrameParameters &op
 
 template <class T>
 int VideoProcessor::DumpFrame(T *output, FrameParameters options, std::shared_ptr<FILE> dumpFile) {
+    PUSH_RANGE("VideoProcessor::DumpFrame", kNvtxYellow);
     int w, h;
     dump_size(options, w, h);
     const size_t n = (size_t)(channelsByFourCC(options.color.dstFourCC) * w * h);
@@ -319,6 +402,12 @@ template int VideoProcessor::DumpFrame(uint8_t *, FrameParameters, std::shared_p
 
 void VideoProcessor::Close() {
     if (isClosed) return;
+    if (ctx && std::getenv("TSVPP_COALESCE_STATS")) {
+        unsigned long long frames = 0, launches = 0;
+        tsvpp_coalesce_stats(ctx, &frames, &launches);
+        std::cout << "coalesce_stats frames " << frames << " launches " << launches << " mean_batch "
+                  << (launches ? (double)frames / (double)launches : 0.0) << "\n" << std::flush;
+    }
     for (auto &item : streamArr) cudaStreamDestroy(item.second);
     streamArr.clear();
     if (ctx) tsvpp_destroy(ctx);

@@ -272,7 +272,7 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
                 for (int cG = 8; cG >= 1; cG >>= 1) {
                     if (want_g && cG != want_g) continue;
                     const int cons = (ctw / 2) * cG;
-                    if (cons > 256) continue;
+                    if (cons > kMarchMaxThreads - 32) continue;
                     const int R = 2 * cG * crpg;
                     if (R > 2 && R >= 2 * round_up(dh, 2)) continue;  // don't over-size strips for short outputs
                     Slots S;

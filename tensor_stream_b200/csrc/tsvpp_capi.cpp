@@ -21,6 +21,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tsvpp.h"
@@ -343,6 +344,25 @@ struct TsvppContext {
     int ring_next = 0;
     std::condition_variable ring_cv;
     std::mutex host_mu;  // tsvpp_convert_batch_host owns hstream / stage_in / stage_out for the whole call
+    // coalescing of per-frame calls (tsvpp_convert_coalesced): requests pending at the same time share a launch
+    struct CoReq {
+        TsvppFrame f;
+        TsvppParams p;
+        void *out = nullptr;
+        int rc = 0;
+        cudaEvent_t ev = nullptr;
+        std::atomic<int> done{0};
+    };
+    static constexpr int kCoEvents = 64;
+    std::mutex co_qmu;       // guards co_q
+    std::vector<CoReq *> co_q;
+    std::mutex co_launch;    // whoever holds it drains co_q and launches (flat combining)
+    std::once_flag co_once;
+    int co_init_rc = 0;
+    cudaStream_t co_stream = nullptr;
+    cudaEvent_t co_ev[kCoEvents] = {};
+    unsigned co_evnext = 0;
+    std::atomic<unsigned long long> co_frames{0}, co_launches{0};
     // host-buffer path
     cudaStream_t hstream[2] = {};
     unsigned char *stage_in[2] = {};
@@ -1011,6 +1031,9 @@ void tsvpp_destroy(TsvppContext *ctx) {
             if (ctx->ring_dev[i]) cudaFree(ctx->ring_dev[i]);
             if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
         }
+        for (int i = 0; i < TsvppContext::kCoEvents; ++i)
+            if (ctx->co_ev[i]) cudaEventDestroy(ctx->co_ev[i]);
+        if (ctx->co_stream) cudaStreamDestroy(ctx->co_stream);
         for (int i = 0; i < 2; ++i) {
             if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
             if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
@@ -1214,6 +1237,113 @@ int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, cons
         TSVPP_ON_DEVICE(ctx);
         return convert_batch_impl(ctx, frames, n, p, out, (cudaStream_t)stream, false);
     }, __LINE__);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Coalescing of per-frame calls.  The reference's pipeline calls VideoProcessor::Convert once per
+// Decoder::GetFrame from up to maxConsumers threads (src/Wrappers/WrapperPython.cpp:265-350, src/Decoder.cpp:97-131);
+// a launch per frame tops out far below what one launch over a batch delivers.  Here every caller posts its
+// frame to a queue and whichever caller holds the launch lock converts everything pending with ONE fused launch
+// per (geometry, parameters) group on the context's coalescing stream ("flat combining": no timer, no extra
+// thread -- while one launch is being issued the next batch accumulates).
+// ---------------------------------------------------------------------------------------------------------
+static int co_init(TsvppContext *ctx) {
+    std::call_once(ctx->co_once, [ctx] {
+        // a blocking stream, like the reference's per-consumer streams (src/VideoProcessor.cpp:86): implicitly ordered
+        // against the legacy default stream
+        cudaError_t e = cudaStreamCreate(&ctx->co_stream);
+        for (int i = 0; i < TsvppContext::kCoEvents && e == cudaSuccess; ++i)
+            e = cudaEventCreateWithFlags(&ctx->co_ev[i], cudaEventDisableTiming);
+        ctx->co_init_rc = (int)e;
+    });
+    return ctx->co_init_rc;
+}
+
+static bool co_same_group(const TsvppContext::CoReq *a, const TsvppContext::CoReq *b) {
+    return a->f.width == b->f.width && a->f.height == b->f.height && a->f.pitch_y == b->f.pitch_y &&
+           a->f.pitch_uv == b->f.pitch_uv && std::memcmp(&a->p, &b->p, sizeof(TsvppParams)) == 0;
+}
+
+// called with ctx->co_launch held
+static void co_drain(TsvppContext *ctx) {
+    std::vector<TsvppContext::CoReq *> batch;
+    {
+        std::lock_guard<std::mutex> lk(ctx->co_qmu);
+        batch.swap(ctx->co_q);
+    }
+    if (batch.empty()) return;
+    std::vector<char> taken(batch.size(), 0);
+    std::vector<TsvppFrame> frames;
+    std::vector<void *> outs;
+    std::vector<size_t> members;
+    for (size_t i = 0; i < batch.size(); ++i) {
+        if (taken[i]) continue;
+        frames.clear(); outs.clear(); members.clear();
+        for (size_t k = i; k < batch.size(); ++k)
+            if (!taken[k] && co_same_group(batch[i], batch[k])) {
+                taken[k] = 1;
+                frames.push_back(batch[k]->f);
+                outs.push_back(batch[k]->out);
+                members.push_back(k);
+            }
+        int rc;
+        try {
+            rc = convert_batch_impl(ctx, frames.data(), (int)frames.size(), &batch[i]->p, outs.data(), ctx->co_stream, false);
+        } catch (...) {
+            rc = note_error(TSVPP_ERROR, "C++ exception in a coalesced launch", __LINE__);
+        }
+        cudaEvent_t ev = ctx->co_ev[ctx->co_evnext++ % TsvppContext::kCoEvents];
+        if (rc == TSVPP_OK && cudaEventRecord(ev, ctx->co_stream) != cudaSuccess) rc = (int)cudaGetLastError();
+        ctx->co_frames.fetch_add(frames.size());
+        ctx->co_launches.fetch_add(1);
+        for (size_t k : members) {
+            batch[k]->rc = rc;
+            batch[k]->ev = ev;
+            batch[k]->done.store(1, std::memory_order_release);  // the request lives on its caller's stack: last touch
+        }
+    }
+}
+
+void *tsvpp_coalesce_stream(TsvppContext *ctx) {
+    if (!ctx) return nullptr;
+    DeviceGuard g(ctx->device);
+    if (g.err != cudaSuccess || co_init(ctx) != 0) return nullptr;
+    return (void *)ctx->co_stream;
+}
+
+int tsvpp_convert_coalesced(TsvppContext *ctx, const TsvppFrame *frame, const TsvppParams *p, void *out, int wait) {
+    if (!ctx || !frame || !p || !out) return TSVPP_ERROR;
+    return abi_guard([&]() -> int {
+        TSVPP_ON_DEVICE(ctx);
+        if (int rc = co_init(ctx)) return note_error(rc, "coalescing stream", __LINE__);
+        TsvppContext::CoReq r;
+        r.f = *frame;
+        r.p = *p;
+        r.out = out;
+        {
+            std::lock_guard<std::mutex> lk(ctx->co_qmu);
+            ctx->co_q.push_back(&r);
+        }
+        for (unsigned spins = 0; !r.done.load(std::memory_order_acquire); ++spins) {
+            if (ctx->co_launch.try_lock()) {
+                co_drain(ctx);
+                ctx->co_launch.unlock();
+            } else if (spins > 64) {
+                std::this_thread::yield();
+            }
+        }
+        if (r.rc) return r.rc;
+        if (wait) TSVPP_CUDA(cudaEventSynchronize(r.ev));
+        return TSVPP_OK;
+    }, __LINE__);
+}
+
+int tsvpp_coalesce_stats(const TsvppContext *ctx, unsigned long long *frames, unsigned long long *launches) {
+    if (!ctx) return TSVPP_ERROR;
+    if (frames) *frames = ctx->co_frames.load();
+    if (launches) *launches = ctx->co_launches.load();
+    return TSVPP_OK;
 }
 
 int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,

@@ -29,7 +29,10 @@ namespace tsvpp {
 
 enum MarchMode : int { MARCH_BICUBIC = 0, MARCH_AREA = 1 };
 
-constexpr int kMarchMaxThreads = 288;  // 1 producer warp + up to 256 consumers
+#ifndef TSVPP_MARCH_MAXTHREADS
+#define TSVPP_MARCH_MAXTHREADS 288
+#endif
+constexpr int kMarchMaxThreads = TSVPP_MARCH_MAXTHREADS;  // 1 producer warp + up to 256 consumers
 
 // bicubic: one record per luma column, and one per chroma PAIR (U and V share position and weights)
 struct MarchColB {

@@ -18,6 +18,16 @@
 #include "vpp_device.cuh"
 #include "vpp_march.h"
 
+// CTAs per SM the register allocation is bounded for.  Bicubic: 3 (72 registers, a few spilled words) measured
+// +12 % (C3) / +22 % (1080p -> 2160p) over 2 (96 registers): the dependent dp4a / PRMT chains want the warps more
+// than the registers (gpurun r2c).  Area: 2.
+#ifndef TSVPP_MARCH_MINBLOCKS_BICUBIC
+#define TSVPP_MARCH_MINBLOCKS_BICUBIC 3
+#endif
+#ifndef TSVPP_MARCH_MINBLOCKS_AREA
+#define TSVPP_MARCH_MINBLOCKS_AREA 2
+#endif
+
 namespace tsvpp {
 
 // u8 x s8 and u8 x u8 four-way dot products with 32-bit accumulate (SASS IDP.4A)
@@ -81,10 +91,18 @@ __device__ __forceinline__ uint32_t pack_sat2(int a, int b, uint32_t c) {
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-// the tie path: reference src/Resize.cu:45-51 with its FP64 weights (taps in tap order, one per byte)
-__device__ __forceinline__ int bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps) {
-    return bicubic_dot(__ldg(c), __ldg(c + 1), __ldg(c + 2), __ldg(c + 3), (int)(taps & 0xffu), (int)((taps >> 8) & 0xffu),
-                       (int)((taps >> 16) & 0xffu), (int)(taps >> 24));
+// The tie path: reference src/Resize.cu:45-51 with its FP64 weights (taps in tap order, one per byte), DFMA chain
+// as compiled (vpp_device.cuh: bicubic_dot).  `r` is the integer path's result floor(s_exact + 1/2) = n + 1 with
+// s_exact = n + 1/2: the FP64 sum is within 1e-10 of that, so round-half-away of it is n + 1 if it is >= n + 1/2
+// and n otherwise (n + 1/2 is exact in FP64; for n < 0 both clamp to 0) -- no libdevice round() needed.
+__device__ __forceinline__ int bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps, int r) {
+    const double2 c01 = __ldg(reinterpret_cast<const double2 *>(c));
+    const double2 c23 = __ldg(reinterpret_cast<const double2 *>(c) + 1);
+    double s = __dmul_rn(c01.y, (double)(int)((taps >> 8) & 0xffu));
+    s = __fma_rn(c01.x, (double)(int)(taps & 0xffu), s);
+    s = __fma_rn(c23.x, (double)(int)((taps >> 16) & 0xffu), s);
+    s = __fma_rn(c23.y, (double)(int)(taps >> 24), s);
+    return s >= (double)r - 0.5 ? r : r - 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -187,6 +205,10 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
     const MarchRowB *rowl = reinterpret_cast<const MarchRowB *>(P.row_l);
     const MarchRowB *rowc = reinterpret_cast<const MarchRowB *>(P.row_c);
     const double *cxd = P.cxd, *cyd = P.cyd;
+    // the RGB family takes its samples as kMagicBits | value (the float 2^23 + value): one PRMT either way
+    constexpr bool MAGIC = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32 || OK == OUT_NV12_U8 || OK == OUT_NV12_F32);
+    constexpr uint32_t kHi = MAGIC ? kMagicBits : 0u;
+    constexpr uint32_t kSelA = MAGIC ? 0x7541u : 0x4441u;  // {byte 1 of the pack, 0, 0, 0x4B | 0}
     QConst qx, qy;
     qx.set(P.qx, XL);
     qy.set(P.qy, YL);
@@ -204,10 +226,10 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         int rA0 = idot_raw<XL>(tA0, bc.w0, qx, zA0), rA1 = idot_raw<XL>(tA1, bc.w1, qx, zA1);
         int rB0 = idot_raw<XL>(tB0, bc.w0, qx, zB0), rB1 = idot_raw<XL>(tB1, bc.w1, qx, zB1);
         if ((((zA0 | zB0) ? 1 : 0) | ((zA1 | zB1) ? 2 : 0)) & bc.inexact) {
-            if (zA0 && (bc.inexact & 1)) rA0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tA0);
-            if (zB0 && (bc.inexact & 1)) rB0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tB0);
-            if (zA1 && (bc.inexact & 2)) rA1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tA1);
-            if (zB1 && (bc.inexact & 2)) rB1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tB1);
+            if (zA0 && (bc.inexact & 1)) rA0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tA0, rA0);
+            if (zB0 && (bc.inexact & 1)) rB0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tB0, rB0);
+            if (zA1 && (bc.inexact & 2)) rA1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tA1, rA1);
+            if (zB1 && (bc.inexact & 2)) rB1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tB1, rB1);
         }
         W0 = pack_sat2(rA0, rB0, W0);
         W1 = pack_sat2(rA1, rB1, W1);
@@ -219,8 +241,8 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         bool zA0, zA1;
         int rA0 = idot_raw<XL>(tA0, bc.w0, qx, zA0), rA1 = idot_raw<XL>(tA1, bc.w1, qx, zA1);
         if (((zA0 ? 1 : 0) | (zA1 ? 2 : 0)) & bc.inexact) {
-            if (zA0 && (bc.inexact & 1)) rA0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tA0);
-            if (zA1 && (bc.inexact & 2)) rA1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tA1);
+            if (zA0 && (bc.inexact & 1)) rA0 = bicubic_tie_fp64(cxd + 4 * (size_t)j0, tA0, rA0);
+            if (zA1 && (bc.inexact & 2)) rA1 = bicubic_tie_fp64(cxd + 4 * (size_t)(j0 + 1), tA1, rA1);
         }
         W0 = __byte_perm(W0, clamp_u8(rA0), 0x2104);  // (W << 8) | new
         W1 = __byte_perm(W1, clamp_u8(rA1), 0x2104);
@@ -240,10 +262,10 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         int rUB = idot_raw<XL>(uB, bc.wc, qx, z2), rVB = idot_raw<XL>(vB, bc.wc, qx, z3);
         if ((z0 | z1 | z2 | z3) && (bc.inexact & 4)) {
             const double *cd = cxd + 4 * (size_t)(j0 >> 1);
-            if (z0) rUA = bicubic_tie_fp64(cd, uA);
-            if (z1) rVA = bicubic_tie_fp64(cd, vA);
-            if (z2) rUB = bicubic_tie_fp64(cd, uB);
-            if (z3) rVB = bicubic_tie_fp64(cd, vB);
+            if (z0) rUA = bicubic_tie_fp64(cd, uA, rUA);
+            if (z1) rVA = bicubic_tie_fp64(cd, vA, rVA);
+            if (z2) rUB = bicubic_tie_fp64(cd, uB, rUB);
+            if (z3) rVB = bicubic_tie_fp64(cd, vB, rVB);
         }
         WU = pack_sat2(rUA, rUB, WU);
         WV = pack_sat2(rVA, rVB, WV);
@@ -255,16 +277,21 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         int rUA = idot_raw<XL>(uA, bc.wc, qx, z0), rVA = idot_raw<XL>(vA, bc.wc, qx, z1);
         if ((z0 | z1) && (bc.inexact & 4)) {
             const double *cd = cxd + 4 * (size_t)(j0 >> 1);
-            if (z0) rUA = bicubic_tie_fp64(cd, uA);
-            if (z1) rVA = bicubic_tie_fp64(cd, vA);
+            if (z0) rUA = bicubic_tie_fp64(cd, uA, rUA);
+            if (z1) rVA = bicubic_tie_fp64(cd, vA, rVA);
         }
         WU = __byte_perm(WU, clamp_u8(rUA), 0x2104);
         WV = __byte_perm(WV, clamp_u8(rVA), 0x2104);
     };
     // row records: first 16 bytes {meta, -, w0, w1}, next 16 {w2, w3, -, -} (read for long vertical digits only)
     auto load_row = [&](const MarchRowB *r, int4 &lo, int4 &hi) {
-        lo = __ldg(reinterpret_cast<const int4 *>(r));
-        if (YL) hi = __ldg(reinterpret_cast<const int4 *>(r) + 1);
+        // volatile: the loads stay where they are written (requested a row ahead, consumed late) instead of being
+        // sunk to their first use
+        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(r));
+        if (YL)
+            asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                         : "l"(reinterpret_cast<const int4 *>(r) + 1));
     };
     // vertical sums of two windows that share a row record; tie path with the row's FP64 weights
     auto vsum2 = [&](uint32_t Wa, uint32_t Wb, const int4 &lo, const int4 &hi, const double *cd, int &ra, int &rb) {
@@ -275,11 +302,12 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         const uint32_t meta = (uint32_t)lo.x;
         if ((za | zb) && !(meta >> 28)) {
             const uint32_t tapsel = (meta >> 12) & 0xffffu;  // window bytes back into tap order
-            if (za) ra = bicubic_tie_fp64(cd, __byte_perm(Wa, 0u, tapsel));
-            if (zb) rb = bicubic_tie_fp64(cd, __byte_perm(Wb, 0u, tapsel));
+            if (za) ra = bicubic_tie_fp64(cd, __byte_perm(Wa, 0u, tapsel), ra);
+            if (zb) rb = bicubic_tie_fp64(cd, __byte_perm(Wb, 0u, tapsel), rb);
         }
-        ra = (int)clamp_u8(ra);
-        rb = (int)clamp_u8(rb);
+        const uint32_t pk = pack_sat2(ra, rb, 0u);  // byte 1 = clamp(ra), byte 0 = clamp(rb)
+        ra = (int)__byte_perm(pk, kHi, kSelA);
+        rb = (int)__byte_perm(pk, kHi, kSelA - 1u);
     };
 
     uint32_t WY0 = 0, WY1 = 0, WU = 0, WV = 0;
@@ -298,7 +326,7 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         load_row(rowl + i0 + 1, rb_lo, rb_hi);
         if (NEED_UV) load_row(rowc + pr, rc_lo, rc_hi);
         int Yv[2][2];
-        int UV[1][2] = {{0, 0}};
+        int UV[1][2] = {{(int)kHi, (int)kHi}};
         {
             int n = (int)((uint32_t)ra_lo.x & 0xfffu) - curl;  // uniform
             curl += n;
@@ -326,9 +354,9 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
         const int nx = min(2, P.e.dw - j0), ny = min(2, dh - i0);
         if (nx > 0) {
             if (nx == 2 && ny == 2 && vec)
-                emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, 2, 2, true);
+                emit_block<OK, 2, MAGIC>(P.e, outp, i0, j0, Yv, UV, 2, 2, true);
             else
-                emit_block<OK, 2>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
+                emit_block<OK, 2, MAGIC>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
         }
     }
 }
@@ -339,7 +367,7 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
 // MODE: MARCH_BICUBIC / MARCH_AREA.  VAR: bicubic: bit 0 = long horizontal digits, bit 1 = long vertical digits;
 // area: NW (1, 2 or 4).
 template <int MODE, int VAR, int OK>
-__global__ void __launch_bounds__(kMarchMaxThreads, 2)
+__global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVPP_MARCH_MINBLOCKS_BICUBIC : TSVPP_MARCH_MINBLOCKS_AREA)
     vpp_march_kernel(const MarchPlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -85,6 +85,14 @@ def load_library():
     L.tsvpp_convert_batch_host.argtypes = [vp, C.POINTER(TsvppFrame), C.c_int, C.POINTER(TsvppParams),
                                            C.POINTER(vp)]
     L.tsvpp_convert_batch_host.restype = C.c_int
+    L.tsvpp_convert_coalesced.argtypes = [vp, C.POINTER(TsvppFrame), C.POINTER(TsvppParams), vp, C.c_int]
+    L.tsvpp_convert_coalesced.restype = C.c_int
+    L.tsvpp_coalesce_stream.argtypes = [vp]
+    L.tsvpp_coalesce_stream.restype = vp
+    L.tsvpp_coalesce_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.tsvpp_coalesce_stats.restype = C.c_int
+    L.tsvpp_plan_cache_size.argtypes = [vp]
+    L.tsvpp_plan_cache_size.restype = C.c_int
     L.tsvpp_last_host_path.argtypes = [vp]
     L.tsvpp_last_host_path.restype = C.c_int
     L.tsvpp_launch_count.argtypes = [vp]
@@ -224,6 +232,24 @@ class VideoProcessor:
 
     def launch_count(self):
         return int(self._L.tsvpp_launch_count(self._h))
+
+    def plan_cache_size(self):
+        return int(self._L.tsvpp_plan_cache_size(self._h))
+
+    def coalesce_stats(self):
+        """(frames, launches) of convert_coalesced so far."""
+        f, l = C.c_ulonglong(), C.c_ulonglong()
+        _check(self._L.tsvpp_coalesce_stats(self._h, C.byref(f), C.byref(l)))
+        return int(f.value), int(l.value)
+
+    def convert_coalesced(self, y, uv, params, out, width=None, height=None, wait=True):
+        """One frame per call, callable from many threads at once (the reference's getFrame pattern): calls
+        pending at the same time share ONE fused launch on the context's coalescing stream.  `out` is a
+        preallocated CUDA tensor; with wait=False the call returns once the covering launch is enqueued."""
+        f = self._frame_struct(y, uv, width, height)
+        p = params.c
+        _check(self._L.tsvpp_convert_coalesced(self._h, C.byref(f), C.byref(p), C.c_void_p(out.data_ptr()), 1 if wait else 0))
+        return out
 
     # -- the hot path ---------------------------------------------------------------------
     def convert_batch(self, frames, params, out=None, widths=None, stream=None):
