@@ -99,6 +99,16 @@ public:
     // output->opaque receives a fresh device buffer (stream-ordered allocation, cudaFree-able
     // by the caller exactly like the reference's), output->width/height the final size.
     int Convert(AVFrame *input, AVFrame *output, FrameParameters &options, std::string consumerName);
+    // --- extensions (not in the reference) for pipelines beyond ~1e5 frames/s ---------------------------------
+    // Convert() hands out a fresh allocation per frame which the caller releases with cudaFree(): two driver calls
+    // per frame that serialise across threads.  ConvertInto() writes into a buffer the CALLER owns (a tensor from
+    // torch's caching allocator in the ATen hand-off, a recycled pool in tests/cpp/ring_main.cpp): `dst` must hold
+    // channelsByFourCC * w * h elements and be usable on CoalescingStream().  Same dispatch, same bits, same
+    // coalescing; no CUDA call on the caller's thread.  Returns like Convert(); output->opaque = dst.
+    int ConvertInto(AVFrame *input, AVFrame *output, void *dst, FrameParameters &options, std::string consumerName);
+    // the stream coalesced conversions run on (blocking stream), and a wait for everything issued on it so far
+    cudaStream_t CoalescingStream() const { return coStream; }
+    int WaitCoalesced();
     template <class T>
     int DumpFrame(T *output, FrameParameters options, std::shared_ptr<FILE> dumpFile);
     void Close();
@@ -117,4 +127,5 @@ private:
     // (tsvpp_convert_coalesced); TSVPP_COALESCE=0 at Init keeps one launch per call on the consumer's own stream.
     bool coalesce = true;
     cudaStream_t coStream = nullptr;
+    int convertImpl(AVFrame *input, AVFrame *output, void *callerDst, FrameParameters &options, const std::string &consumerName);
 };

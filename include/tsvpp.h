@@ -96,13 +96,20 @@ void tsvpp_batch_destroy(TsvppBatch *batch);
  * TensorStream::getFrame -> VideoProcessor::Convert, src/Wrappers/WrapperPython.cpp:265-350): calls that are pending
  * at the same time and agree on geometry and parameters are converted by ONE fused launch on the context's
  * coalescing stream.  `out` must be usable on that stream (e.g. cudaMallocAsync'd on tsvpp_coalesce_stream()).
- * wait != 0: return when this frame's result is complete; wait == 0: return once the launch that covers it has been
+ * wait > 0: return when this frame's result is complete; wait == 0: return once the launch that covers it has been
  * issued (stream-ordered; the coalescing stream is a blocking stream, so work on the legacy default stream is
- * ordered after it like after the reference's per-consumer streams). */
+ * ordered after it like after the reference's per-consumer streams); wait < 0 ("posted"): return at once -- the
+ * frame is picked up by the context's launcher thread; the input planes and `out` must stay untouched until
+ * tsvpp_coalesce_wait() returns, which also reports the first error of a posted frame. */
 int tsvpp_convert_coalesced(TsvppContext *ctx, const TsvppFrame *frame, const TsvppParams *p, void *out, int wait);
 void *tsvpp_coalesce_stream(TsvppContext *ctx);
+/* Returns when every coalesced frame issued so far is complete (wait == 0 callers use it before they reuse or read
+ * their outputs on the host). */
+int tsvpp_coalesce_wait(TsvppContext *ctx);
 /* frames converted / launches issued by tsvpp_convert_coalesced so far (their ratio is the mean batch size) */
 int tsvpp_coalesce_stats(const TsvppContext *ctx, unsigned long long *frames, unsigned long long *launches);
+/* host nanoseconds spent issuing those launches (plan lookup + descriptor upload + launch + event record) */
+unsigned long long tsvpp_coalesce_issue_ns(const TsvppContext *ctx);
 
 /* End-to-end entry with HOST buffers: each frame is a host NV12 image (y: height*pitch_y bytes,
  * uv: height/2*pitch_uv bytes); outputs are written to host memory.  Copies are pipelined with

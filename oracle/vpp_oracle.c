@@ -8,7 +8,7 @@
  *
  * Parity status: PINNED.  tests/test_oracle_golden.py checks this file against the
  * reference's own golden CRC-32 values (tests/src/VPPTests.cpp, PythonTests.cpp) and its
- * seven float32 golden dumps (tests/resources/test_references), and tests/test_parity_ref.py
+ * seven float32 golden dumps (tests/resources/test_references), and tests/test_parity_gpu.py (test_reference_vpp_equals_oracle)
  * (GPU) checks it against the reference's unmodified .cu files compiled for sm_100a
  * (oracle/_ref).
  *

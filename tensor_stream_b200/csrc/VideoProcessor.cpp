@@ -311,6 +311,19 @@ int VideoProcessor::Init(std::shared_ptr<Logger> lg, uint8_t maxConsumers, bool 
 
 int VideoProcessor::Convert(AVFrame *input, AVFrame *output, FrameParameters &options, std::string consumerName) {
     PUSH_RANGE("VideoProcessor::Convert", kNvtxYellow);
+    return convertImpl(input, output, nullptr, options, consumerName);
+}
+
+int VideoProcessor::ConvertInto(AVFrame *input, AVFrame *output, void *dst, FrameParameters &options, std::string consumerName) {
+    PUSH_RANGE("VideoProcessor::ConvertInto", kNvtxYellow);
+    if (!dst) return VREADER_ERROR;
+    return convertImpl(input, output, dst, options, consumerName);
+}
+
+int VideoProcessor::WaitCoalesced() { return (ctx && coalesce) ? tsvpp_coalesce_wait(ctx) : VREADER_OK; }
+
+int VideoProcessor::convertImpl(AVFrame *input, AVFrame *output, void *callerDst, FrameParameters &options,
+                                const std::string &consumerName) {
     if (isClosed || !ctx) return VREADER_ERROR;
     cudaStream_t stream;
     {
@@ -332,29 +345,36 @@ int VideoProcessor::Convert(AVFrame *input, AVFrame *output, FrameParameters &op
     if (rc) return rc;
     // The reference's Convert returns with the work complete in every resize/crop path (its
     // cudaFree calls synchronise the device).  Keep that guarantee unless the caller opts out.
-    static const bool async_mode = [] {
+    // TSVPP_ASYNC: 0 (default) complete on return; 1 return once the launch is issued (stream-ordered); 2 posted --
+    // return at once, results are valid after WaitCoalesced() (inputs must stay alive until then)
+    static const int async_level = [] {
         const char *s = std::getenv("TSVPP_ASYNC");
-        return s && *s == '1';
+        return (s && *s >= '0' && *s <= '2') ? *s - '0' : 0;
     }();
-    void *dst = nullptr;
+    const bool async_mode = async_level != 0;
+    void *dst = callerDst;
     cudaError_t e;
     if (coalesce) {
         // the result buffer is allocated on the coalescing stream by the caller's own thread (stream-ordered, no
         // lock of ours), then the frame joins whatever launch is being assembled
-        e = cudaMallocAsync(&dst, elems * (size_t)es, coStream);
-        if (e != cudaSuccess) return (int)e;
-        rc = tsvpp_convert_coalesced(ctx, &f, &p, dst, async_mode ? 0 : 1);
+        if (!callerDst) {
+            e = cudaMallocAsync(&dst, elems * (size_t)es, coStream);
+            if (e != cudaSuccess) return (int)e;
+        }
+        rc = tsvpp_convert_coalesced(ctx, &f, &p, dst, async_level == 0 ? 1 : async_level == 1 ? 0 : -1);
         if (rc) {
-            cudaFreeAsync(dst, coStream);
+            if (!callerDst) cudaFreeAsync(dst, coStream);
             return rc;
         }
     } else {
-        e = cudaMallocAsync(&dst, elems * (size_t)es, stream);
-        if (e != cudaSuccess) return (int)e;
+        if (!callerDst) {
+            e = cudaMallocAsync(&dst, elems * (size_t)es, stream);
+            if (e != cudaSuccess) return (int)e;
+        }
         void *outs[1] = {dst};
         rc = tsvpp_convert_batch(ctx, &f, 1, &p, outs, stream);
         if (rc) {
-            cudaFreeAsync(dst, stream);
+            if (!callerDst) cudaFreeAsync(dst, stream);
             return rc;
         }
         if (!async_mode) {
@@ -406,7 +426,8 @@ void VideoProcessor::Close() {
         unsigned long long frames = 0, launches = 0;
         tsvpp_coalesce_stats(ctx, &frames, &launches);
         std::cout << "coalesce_stats frames " << frames << " launches " << launches << " mean_batch "
-                  << (launches ? (double)frames / (double)launches : 0.0) << "\n" << std::flush;
+                  << (launches ? (double)frames / (double)launches : 0.0) << " issue_us_per_launch "
+                  << (launches ? (double)tsvpp_coalesce_issue_ns(ctx) / 1e3 / (double)launches : 0.0) << "\n" << std::flush;
     }
     for (auto &item : streamArr) cudaStreamDestroy(item.second);
     streamArr.clear();

@@ -6,10 +6,12 @@
 // into tables instead of per pixel per frame.  All float math here mirrors the device arithmetic
 // of the reference bit for bit: fmaf() where nvcc contracted, plain IEEE ops elsewhere; this file
 // is compiled with -ffp-contract=off.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -350,10 +352,12 @@ struct TsvppContext {
         TsvppParams p;
         void *out = nullptr;
         int rc = 0;
-        cudaEvent_t ev = nullptr;
+        unsigned seq = 0;            // completion ticket (stream memory-op path)
+        cudaEvent_t ev = nullptr;    // completion event (fallback path)
         std::atomic<int> done{0};
     };
     static constexpr int kCoEvents = 64;
+    static constexpr int kCoSlots = 32;
     std::mutex co_qmu;       // guards co_q
     std::vector<CoReq *> co_q;
     std::mutex co_launch;    // whoever holds it drains co_q and launches (flat combining)
@@ -362,7 +366,46 @@ struct TsvppContext {
     cudaStream_t co_stream = nullptr;
     cudaEvent_t co_ev[kCoEvents] = {};
     unsigned co_evnext = 0;
-    std::atomic<unsigned long long> co_frames{0}, co_launches{0};
+    // Completion tickets: after every coalesced launch the stream writes the launch's sequence number into a pinned
+    // host word (cuStreamWriteValue32).  Waiters and descriptor-slot reuse poll that word -- no CUDA call per frame,
+    // which matters because driver calls from many threads serialise on the context lock (measured: 8 consumers each
+    // calling cudaMallocAsync / cudaEventSynchronize stretch a 10 us launch path to 40 us).
+    bool co_memops = false;
+    // cuStreamWriteValue32, resolved through the runtime (cudaGetDriverEntryPoint): the library must load on machines
+    // without a driver (CPU-only build / export checks), so it does not link libcuda
+    CUresult (*co_write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    volatile unsigned *co_done_host = nullptr;
+    CUdeviceptr co_done_dev = 0;
+    unsigned co_seq = 0;  // last ticket issued (launch lock held)
+    std::atomic<unsigned> co_seq_pub{0};  // the same, readable without the lock
+    // Launcher thread (default; TSVPP_CO_THREAD=0 lets the callers combine among themselves instead): one thread
+    // drains the queue and issues the launches, so the issue path stays on one core with warm caches and the callers
+    // never touch the driver.  It spins while frames keep coming and sleeps on a condition variable when idle.
+    bool co_use_thread = false;
+    std::thread co_thread;
+    std::atomic<bool> co_stop{false};
+    std::atomic<int> co_pending{0};
+    std::atomic<int> co_sleeping{0};
+    std::mutex co_cv_mu;
+    std::condition_variable co_cv;
+    // posted requests (wait < 0): copied into the queue, the caller does not wait for the launch to be issued
+    struct CoPosted {
+        TsvppFrame f;
+        TsvppParams p;
+        void *out;
+    };
+    std::vector<CoPosted> co_qp;      // guarded by co_qmu
+    std::atomic<int> co_posted_rc{0};  // first error of a posted frame, reported by tsvpp_coalesce_wait
+    std::atomic<unsigned long long> co_posted_total{0}, co_posted_issued{0};  // frames posted / posted frames launched
+    struct CoSlot {
+        FrameDev *host = nullptr, *dev = nullptr;
+        FrameDev *host_dev = nullptr;  // device address of the (mapped) pinned host copy
+        int cap = 0;
+        unsigned seq = 0;
+        bool used = false;
+    } co_slot[kCoSlots];
+    unsigned co_slotnext = 0;
+    std::atomic<unsigned long long> co_frames{0}, co_launches{0}, co_drain_ns{0};
     // host-buffer path
     cudaStream_t hstream[2] = {};
     unsigned char *stage_in[2] = {};
@@ -1023,6 +1066,14 @@ int tsvpp_create(int device, TsvppContext **out) {
 
 void tsvpp_destroy(TsvppContext *ctx) {
     if (!ctx) return;
+    if (ctx->co_thread.joinable()) {
+        ctx->co_stop.store(true, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(ctx->co_cv_mu);
+            ctx->co_cv.notify_all();
+        }
+        ctx->co_thread.join();
+    }
     {
         DeviceGuard g(ctx->device);
         cudaDeviceSynchronize();
@@ -1034,6 +1085,11 @@ void tsvpp_destroy(TsvppContext *ctx) {
         for (int i = 0; i < TsvppContext::kCoEvents; ++i)
             if (ctx->co_ev[i]) cudaEventDestroy(ctx->co_ev[i]);
         if (ctx->co_stream) cudaStreamDestroy(ctx->co_stream);
+        if (ctx->co_done_host) cudaFreeHost((void *)ctx->co_done_host);
+        for (auto &sl : ctx->co_slot) {
+            if (sl.host) cudaFreeHost(sl.host);
+            if (sl.dev) cudaFree(sl.dev);
+        }
         for (int i = 0; i < 2; ++i) {
             if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
             if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
@@ -1248,6 +1304,8 @@ int tsvpp_convert_batch(TsvppContext *ctx, const TsvppFrame *frames, int n, cons
 // per (geometry, parameters) group on the context's coalescing stream ("flat combining": no timer, no extra
 // thread -- while one launch is being issued the next batch accumulates).
 // ---------------------------------------------------------------------------------------------------------
+static void co_thread_main(TsvppContext *ctx);
+
 static int co_init(TsvppContext *ctx) {
     std::call_once(ctx->co_once, [ctx] {
         // a blocking stream, like the reference's per-consumer streams (src/VideoProcessor.cpp:86): implicitly ordered
@@ -1255,9 +1313,72 @@ static int co_init(TsvppContext *ctx) {
         cudaError_t e = cudaStreamCreate(&ctx->co_stream);
         for (int i = 0; i < TsvppContext::kCoEvents && e == cudaSuccess; ++i)
             e = cudaEventCreateWithFlags(&ctx->co_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess && !env_int("TSVPP_CO_EVENTS", 0)) {
+            void *h = nullptr, *d = nullptr;
+            if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+                *(volatile unsigned *)h = 0u;
+                void *fn = nullptr;
+                cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+                if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+                    qres != cudaDriverEntryPointSuccess)
+                    fn = nullptr;
+                ctx->co_write32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fn);
+                // one trial write decides between tickets and events
+                if (ctx->co_write32 && ctx->co_write32((CUstream)ctx->co_stream, (CUdeviceptr)d, 0u, 0) == CUDA_SUCCESS &&
+                    cudaStreamSynchronize(ctx->co_stream) == cudaSuccess) {
+                    ctx->co_done_host = (volatile unsigned *)h;
+                    ctx->co_done_dev = (CUdeviceptr)d;
+                    ctx->co_memops = true;
+                } else {
+                    (void)cudaGetLastError();
+                    cudaFreeHost(h);
+                }
+            } else {
+                (void)cudaGetLastError();
+                if (h) cudaFreeHost(h);
+            }
+        }
         ctx->co_init_rc = (int)e;
+        if (e == cudaSuccess && env_int("TSVPP_CO_THREAD", 1)) {
+            ctx->co_use_thread = true;
+            ctx->co_thread = std::thread(co_thread_main, ctx);
+        }
     });
     return ctx->co_init_rc;
+}
+
+static void co_drain(TsvppContext *ctx);
+static inline bool co_reached(const TsvppContext *ctx, unsigned seq);
+
+static void co_thread_main(TsvppContext *ctx) {
+    cudaSetDevice(ctx->device);
+    const unsigned depth = (unsigned)std::max(1, env_int("TSVPP_CO_DEPTH", 2));
+    unsigned idle = 0;
+    while (!ctx->co_stop.load(std::memory_order_acquire)) {
+        if (ctx->co_pending.load(std::memory_order_acquire) > 0) {
+            // at most `depth` launches in flight: while the stream is that far behind, let the queue grow
+            if (ctx->co_memops && !co_reached(ctx, ctx->co_seq - (depth - 1))) continue;
+            std::lock_guard<std::mutex> lk(ctx->co_launch);
+            co_drain(ctx);
+            idle = 0;
+        } else if (++idle > 20000) {  // ~100 us without work: sleep until the next frame is posted
+            std::unique_lock<std::mutex> lk(ctx->co_cv_mu);
+            ctx->co_sleeping.store(1, std::memory_order_release);
+            ctx->co_cv.wait_for(lk, std::chrono::milliseconds(50), [ctx] {
+                return ctx->co_pending.load(std::memory_order_acquire) > 0 || ctx->co_stop.load(std::memory_order_acquire);
+            });
+            ctx->co_sleeping.store(0, std::memory_order_release);
+            idle = 0;
+        }
+    }
+}
+
+static inline bool co_reached(const TsvppContext *ctx, unsigned seq) {
+    return (int)(*ctx->co_done_host - seq) >= 0;  // wrap-safe
+}
+static inline void co_spin_until(const TsvppContext *ctx, unsigned seq) {
+    for (unsigned spins = 0; !co_reached(ctx, seq); ++spins)
+        if (spins > 2000) std::this_thread::yield();
 }
 
 static bool co_same_group(const TsvppContext::CoReq *a, const TsvppContext::CoReq *b) {
@@ -1265,14 +1386,78 @@ static bool co_same_group(const TsvppContext::CoReq *a, const TsvppContext::CoRe
            a->f.pitch_uv == b->f.pitch_uv && std::memcmp(&a->p, &b->p, sizeof(TsvppParams)) == 0;
 }
 
+// one group through the ticket path: descriptor slot of the coalescer's own ring, one launch, one stream write
+static int co_launch_group(TsvppContext *ctx, const TsvppFrame *frames, void *const *outs, int n, const TsvppParams *p,
+                           unsigned *seq_out) {
+    int rc = check_uniform(frames, n);
+    if (rc) return rc;
+    const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
+    std::shared_ptr<Plan> pl;
+    rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+    if (rc) return rc;
+    TsvppContext::CoSlot &sl = ctx->co_slot[ctx->co_slotnext++ % TsvppContext::kCoSlots];
+    if (sl.used) co_spin_until(ctx, sl.seq);  // the launch that read this slot has completed
+    if (sl.cap < n) {
+        if (sl.host) cudaFreeHost(sl.host);
+        if (sl.dev) cudaFree(sl.dev);
+        sl.host = sl.dev = sl.host_dev = nullptr;
+        sl.cap = 0;
+        const int cap = std::max(64, n);
+        TSVPP_CUDA(cudaHostAlloc(&sl.host, sizeof(FrameDev) * cap, cudaHostAllocMapped));
+        TSVPP_CUDA(cudaHostGetDevicePointer(&sl.host_dev, sl.host, 0));
+        TSVPP_CUDA(cudaMalloc(&sl.dev, sizeof(FrameDev) * cap));
+        sl.cap = cap;
+    }
+    for (int i = 0; i < n; ++i) {
+        sl.host[i].y = frames[i].y;
+        sl.host[i].uv = frames[i].uv;
+        sl.host[i].out = outs[i];
+    }
+    // Small batches: the kernel reads the few descriptors straight from the mapped pinned copy (one PCIe read per
+    // CTA, ~1.5 us) -- a stream-ordered H2D copy in front of every launch costs more than that on the GPU side and is
+    // one more driver call.  Large batches amortise the copy.
+    const FrameDev *descs = sl.host_dev;
+    if (n > env_int("TSVPP_CO_ZEROCOPY_MAX", 0)) {
+        TSVPP_CUDA(cudaMemcpyAsync(sl.dev, sl.host, sizeof(FrameDev) * n, cudaMemcpyHostToDevice, ctx->co_stream));
+        descs = sl.dev;
+    }
+    (void)cudaGetLastError();
+    rc = launch_plan(pl.get(), descs, n, vec_ok_for(pl.get(), outs, n), grid_for(ctx, pl.get(), n), ctx->co_stream, true);
+    ctx->launches.fetch_add(1);
+    const unsigned seq = ++ctx->co_seq;
+    ctx->co_seq_pub.store(seq, std::memory_order_relaxed);
+    // the ticket is written even after a failed launch: waiters and the slot must not hang on it
+    if (ctx->co_write32((CUstream)ctx->co_stream, ctx->co_done_dev, seq, 0) != CUDA_SUCCESS) {
+        cudaStreamSynchronize(ctx->co_stream);
+        *ctx->co_done_host = seq;
+    }
+    sl.seq = seq;
+    sl.used = true;
+    *seq_out = seq;
+    if (rc) return note_error(rc, "launch (coalesced)", __LINE__);
+    return TSVPP_OK;
+}
+
 // called with ctx->co_launch held
 static void co_drain(TsvppContext *ctx) {
     std::vector<TsvppContext::CoReq *> batch;
+    std::vector<TsvppContext::CoPosted> posted;
     {
         std::lock_guard<std::mutex> lk(ctx->co_qmu);
         batch.swap(ctx->co_q);
+        posted.swap(ctx->co_qp);
     }
-    if (batch.empty()) return;
+    if (batch.empty() && posted.empty()) return;
+    // posted frames join the same groups through stack requests of the draining thread
+    std::vector<TsvppContext::CoReq> carrier(posted.size());
+    for (size_t i = 0; i < posted.size(); ++i) {
+        carrier[i].f = posted[i].f;
+        carrier[i].p = posted[i].p;
+        carrier[i].out = posted[i].out;
+        batch.push_back(&carrier[i]);
+    }
+    const size_t n_waited = batch.size() - posted.size();
+    const auto t_begin = std::chrono::steady_clock::now();
     std::vector<char> taken(batch.size(), 0);
     std::vector<TsvppFrame> frames;
     std::vector<void *> outs;
@@ -1288,21 +1473,38 @@ static void co_drain(TsvppContext *ctx) {
                 members.push_back(k);
             }
         int rc;
+        unsigned seq = 0;
+        cudaEvent_t ev = nullptr;
+        const bool packed = batch[i]->p.fourcc == TSVPP_UYVY || batch[i]->p.fourcc == TSVPP_YUV444;
         try {
-            rc = convert_batch_impl(ctx, frames.data(), (int)frames.size(), &batch[i]->p, outs.data(), ctx->co_stream, false);
+            if (ctx->co_memops && !packed) {
+                rc = co_launch_group(ctx, frames.data(), outs.data(), (int)frames.size(), &batch[i]->p, &seq);
+            } else {
+                rc = convert_batch_impl(ctx, frames.data(), (int)frames.size(), &batch[i]->p, outs.data(), ctx->co_stream, false);
+                ev = ctx->co_ev[ctx->co_evnext++ % TsvppContext::kCoEvents];
+                if (rc == TSVPP_OK && cudaEventRecord(ev, ctx->co_stream) != cudaSuccess) rc = (int)cudaGetLastError();
+            }
         } catch (...) {
             rc = note_error(TSVPP_ERROR, "C++ exception in a coalesced launch", __LINE__);
         }
-        cudaEvent_t ev = ctx->co_ev[ctx->co_evnext++ % TsvppContext::kCoEvents];
-        if (rc == TSVPP_OK && cudaEventRecord(ev, ctx->co_stream) != cudaSuccess) rc = (int)cudaGetLastError();
         ctx->co_frames.fetch_add(frames.size());
         ctx->co_launches.fetch_add(1);
         for (size_t k : members) {
             batch[k]->rc = rc;
+            batch[k]->seq = seq;
             batch[k]->ev = ev;
             batch[k]->done.store(1, std::memory_order_release);  // the request lives on its caller's stack: last touch
         }
     }
+    for (size_t i = n_waited; i < batch.size(); ++i)
+        if (batch[i]->rc) {
+            int expected = 0;
+            ctx->co_posted_rc.compare_exchange_strong(expected, batch[i]->rc);
+        }
+    ctx->co_drain_ns.fetch_add((unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                   std::chrono::steady_clock::now() - t_begin).count());
+    ctx->co_posted_issued.fetch_add(posted.size(), std::memory_order_release);  // after their tickets were issued
+    ctx->co_pending.fetch_sub((int)batch.size(), std::memory_order_acq_rel);
 }
 
 void *tsvpp_coalesce_stream(TsvppContext *ctx) {
@@ -1317,26 +1519,83 @@ int tsvpp_convert_coalesced(TsvppContext *ctx, const TsvppFrame *frame, const Ts
     return abi_guard([&]() -> int {
         TSVPP_ON_DEVICE(ctx);
         if (int rc = co_init(ctx)) return note_error(rc, "coalescing stream", __LINE__);
+        if (wait < 0 && ctx->co_use_thread) {
+            // posted: the launcher thread picks the frame up; nothing to wait for here
+            if (int vrc = validate_geometry(frame->width, frame->height, *p)) return vrc;
+            ctx->co_pending.fetch_add(1, std::memory_order_acq_rel);
+            {
+                std::lock_guard<std::mutex> lk(ctx->co_qmu);
+                ctx->co_qp.push_back(TsvppContext::CoPosted{*frame, *p, out});
+                ctx->co_posted_total.fetch_add(1, std::memory_order_release);
+            }
+            if (ctx->co_sleeping.load(std::memory_order_acquire)) {
+                std::lock_guard<std::mutex> lk(ctx->co_cv_mu);
+                ctx->co_cv.notify_one();
+            }
+            return TSVPP_OK;
+        }
+        if (wait < 0) wait = 0;
         TsvppContext::CoReq r;
         r.f = *frame;
         r.p = *p;
         r.out = out;
+        ctx->co_pending.fetch_add(1, std::memory_order_acq_rel);
         {
             std::lock_guard<std::mutex> lk(ctx->co_qmu);
             ctx->co_q.push_back(&r);
         }
+        if (ctx->co_use_thread) {
+            if (ctx->co_sleeping.load(std::memory_order_acquire)) {
+                std::lock_guard<std::mutex> lk(ctx->co_cv_mu);
+                ctx->co_cv.notify_one();
+            }
+            for (unsigned spins = 0; !r.done.load(std::memory_order_acquire); ++spins)
+                if (spins > 4000) std::this_thread::yield();
+            if (r.rc) return r.rc;
+            if (wait) {
+                if (r.ev) TSVPP_CUDA(cudaEventSynchronize(r.ev));
+                else co_spin_until(ctx, r.seq);
+            }
+            return TSVPP_OK;
+        }
+        // Whoever gets the launch lock converts everything pending.  At most `depth` launches are kept in flight: a
+        // launch issued while the stream is still `depth` launches behind would only queue up, so the would-be
+        // leader lets the queue grow instead -- the batch size adapts to the GPU's per-launch latency (without
+        // this every frame gets its own launch as soon as the issue path is shorter than that latency).
+        const unsigned depth = (unsigned)std::max(1, env_int("TSVPP_CO_DEPTH", 2));
         for (unsigned spins = 0; !r.done.load(std::memory_order_acquire); ++spins) {
-            if (ctx->co_launch.try_lock()) {
+            const bool room = !ctx->co_memops || co_reached(ctx, ctx->co_seq_pub.load(std::memory_order_relaxed) - (depth - 1));
+            if (room && ctx->co_launch.try_lock()) {
                 co_drain(ctx);
                 ctx->co_launch.unlock();
-            } else if (spins > 64) {
+            } else if (spins > 2000) {
                 std::this_thread::yield();
             }
         }
         if (r.rc) return r.rc;
-        if (wait) TSVPP_CUDA(cudaEventSynchronize(r.ev));
+        if (wait) {
+            if (r.ev) TSVPP_CUDA(cudaEventSynchronize(r.ev));
+            else co_spin_until(ctx, r.seq);  // poll the ticket word: no driver call
+        }
         return TSVPP_OK;
     }, __LINE__);
+}
+
+int tsvpp_coalesce_wait(TsvppContext *ctx) {
+    if (!ctx) return TSVPP_ERROR;
+    TSVPP_ON_DEVICE(ctx);
+    if (!ctx->co_stream) return TSVPP_OK;
+    // frames posted before this call: wait until the launcher has issued them (other threads may keep posting),
+    // then for the newest ticket issued by then
+    const unsigned long long target = ctx->co_posted_total.load(std::memory_order_acquire);
+    for (unsigned spins = 0; ctx->co_posted_issued.load(std::memory_order_acquire) < target; ++spins)
+        if (spins > 2000) std::this_thread::yield();
+    if (ctx->co_memops) {
+        co_spin_until(ctx, ctx->co_seq_pub.load(std::memory_order_acquire));
+    } else {
+        TSVPP_CUDA(cudaStreamSynchronize(ctx->co_stream));
+    }
+    return ctx->co_posted_rc.exchange(0);
 }
 
 int tsvpp_coalesce_stats(const TsvppContext *ctx, unsigned long long *frames, unsigned long long *launches) {
@@ -1345,6 +1604,9 @@ int tsvpp_coalesce_stats(const TsvppContext *ctx, unsigned long long *frames, un
     if (launches) *launches = ctx->co_launches.load();
     return TSVPP_OK;
 }
+
+/* nanoseconds spent issuing coalesced launches so far (plan lookup + descriptor upload + launch + event) */
+unsigned long long tsvpp_coalesce_issue_ns(const TsvppContext *ctx) { return ctx ? ctx->co_drain_ns.load() : 0ull; }
 
 int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p, void *const *out,
                        TsvppBatch **batch) {

@@ -341,6 +341,18 @@ def convert_batch_aten(frames, params, widths=None):
                              params.planes_pos.value, params.normalization)
 
 
+def convert_frame_aten(y, uv, params, width=0, height=0, wait=True):
+    """One frame per call through the PyTorch C++ extension, callable from many threads (the GIL is released):
+    the result is an at::empty tensor owned by Python (no use_count() garbage collector, no cudaFree), calls in
+    flight together share one fused launch.  This is the wrapper-shaped replacement of the reference's
+    TensorStream.read() hand-off (src/Wrappers/WrapperPython.cpp:265-350)."""
+    from . import aten_build
+    mod = aten_build.load()
+    return mod.convert_frame(y, uv, int(width or 0), int(height or 0), list(params.crop_coords), params.width, params.height,
+                             params.resize_type.value, params.pixel_format.value, params.planes_pos.value,
+                             params.normalization, bool(wait))
+
+
 def _host_ptr(a):
     if hasattr(a, "data_ptr"):
         return a.data_ptr()

@@ -8,7 +8,12 @@
 //   ring_main semantics                         GetFrame index rules of reference src/Decoder.cpp:97-131
 //   ring_main run <consumers> <frames_per_consumer> <verify 0|1> [fps] [index]
 //                                               prints aggregate frames/s, mean batch size, and (verify) checks every
-//                                               output against a one-frame-per-launch conversion of the same surface
+//                                               output against a one-frame-per-launch conversion of the same surface.
+//                                               fps 0 = the producer runs ahead of the consumers (2 M publishes/s).
+//                                               Results are released the way the reference's callers do, cudaFree()
+//                                               (verify) -- or, RING_FREE=async, stream-ordered with cudaFreeAsync():
+//                                               cudaFree synchronises the device and serialises in the driver, which
+//                                               alone caps ANY per-frame pipeline near 1e5 frames/s.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -112,6 +117,11 @@ int main(int argc, char **argv) {
     const int consumers = std::atoi(argv[2]), per = std::atoi(argv[3]), verify = std::atoi(argv[4]);
     const double fps = argc > 5 ? std::atof(argv[5]) : 0.0;
     const int index = argc > 6 ? std::atoi(argv[6]) : 0;
+    const bool free_async = std::getenv("RING_FREE") && std::string(std::getenv("RING_FREE")) == "async";
+    // RING_OUT=pool: every consumer recycles 32 result buffers of its own through VideoProcessor::ConvertInto (what the
+    // ATen hand-off does with torch's caching allocator) -- no allocation, no free, no CUDA call per frame
+    const bool pool_out = std::getenv("RING_OUT") && std::string(std::getenv("RING_OUT")) == "pool";
+    const int kPoolOut = 32;
     const int W = 1920, H = 1080, pitch = 1920, DW = 256, DH = 256, pool = 64;
     // C2: BGR24 planar 256x256 bilinear, normalised float32
     ColorOptions color(BGR24);
@@ -173,9 +183,11 @@ int main(int argc, char **argv) {
             const int k = (int)(n % pool);
             ring.Publish(surface(ys[k], uvs[k], W, H, pitch));
             published.store(n + 1, std::memory_order_relaxed);
-            if (fps > 0) {
-                const auto due = t0 + std::chrono::duration_cast<clk::duration>(std::chrono::duration<double>((n + 1) / fps));
-                while (clk::now() < due && !stop.load(std::memory_order_relaxed)) std::this_thread::yield();
+            // paced like a decoder; "free-running" still leaves the ring's mutex to the consumers most of the time
+            const double rate = fps > 0 ? fps : 2e6;
+            const auto due = t0 + std::chrono::duration_cast<clk::duration>(std::chrono::duration<double>((n + 1) / rate));
+            while (clk::now() < due && !stop.load(std::memory_order_relaxed)) {
+                if (fps > 0 && fps < 1e5) std::this_thread::yield();
             }
         }
     });
@@ -190,14 +202,25 @@ int main(int argc, char **argv) {
             FrameParameters params = {resize, color, CropOptions()};
             std::vector<void *> held;
             std::vector<int> held_src;
+            std::vector<void *> mine;
+            if (pool_out) {
+                mine.resize(kPoolOut);
+                for (auto &b : mine) CK(cudaMalloc(&b, out_elems * sizeof(float)));
+            }
             std::vector<float> back(verify ? out_elems : 0);
             auto flush = [&] {
+                if (pool_out) vpp.WaitCoalesced();  // before the buffers are read back / written again
                 for (size_t i = 0; i < held.size(); ++i) {
                     if (verify) {
                         CK(cudaMemcpy(back.data(), held[i], out_elems * sizeof(float), cudaMemcpyDeviceToHost));
                         if (std::memcmp(back.data(), expect[held_src[i]].data(), out_elems * sizeof(float)) != 0) bad.fetch_add(1);
                     }
-                    CK(cudaFree(held[i]));  // the caller owns the result and releases it with cudaFree, as with the reference
+                    if (pool_out)
+                        continue;  // recycled
+                    if (free_async)
+                        CK(cudaFreeAsync(held[i], 0));  // stream-ordered: the legacy stream is ordered after the blocking coalescing stream
+                    else
+                        CK(cudaFree(held[i]));  // the caller owns the result and releases it with cudaFree, as with the reference
                 }
                 held.clear();
                 held_src.clear();
@@ -214,16 +237,18 @@ int main(int argc, char **argv) {
                 int src = -1;
                 for (int k = 0; k < pool && src < 0; ++k)
                     if (in.data[0] == ys[k]) src = k;
-                const int rc = vpp.Convert(&in, &out, params, name);
+                const int rc = pool_out ? vpp.ConvertInto(&in, &out, mine[held.size()], params, name)
+                                        : vpp.Convert(&in, &out, params, name);
                 if (rc != VREADER_OK || !out.opaque || out.width != DW || out.height != DH) {
                     bad.fetch_add(1000);
                     break;
                 }
                 held.push_back(out.opaque);
                 held_src.push_back(src);
-                if (held.size() >= 64) flush();
+                if (held.size() >= (pool_out ? (size_t)kPoolOut : free_async ? 16u : 64u)) flush();
             }
             flush();
+            for (auto &b : mine) cudaFree(b);
         });
     for (auto &t : th) t.join();
     CK(cudaDeviceSynchronize());
@@ -232,10 +257,10 @@ int main(int argc, char **argv) {
     ring.notifyConsumers();
     producer.join();
     const double total = (double)consumers * per;
-    std::printf("consumers %d frames %.0f seconds %.4f fps %.0f published %llu repeats %d bad %d coalesce %s async %s\n", consumers,
+    std::printf("consumers %d frames %.0f seconds %.4f fps %.0f published %llu repeats %d bad %d coalesce %s async %s free %s\n", consumers,
                 total, secs, total / secs, published.load(), repeats.load(), bad.load(),
                 std::getenv("TSVPP_COALESCE") ? std::getenv("TSVPP_COALESCE") : "1",
-                std::getenv("TSVPP_ASYNC") ? std::getenv("TSVPP_ASYNC") : "0");
+                std::getenv("TSVPP_ASYNC") ? std::getenv("TSVPP_ASYNC") : "0", pool_out ? "recycled(ConvertInto)" : free_async ? "cudaFreeAsync" : "cudaFree");
     vpp.Close();
     return bad.load() ? 1 : 0;
 }

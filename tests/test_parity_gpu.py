@@ -37,7 +37,9 @@ def vp():
 def refvpp():
     from oracle import refvpp as R
     if not R.available():
-        pytest.skip("oracle/_ref not built")
+        # the compiled reference is the GPU oracle of record: its absence must not pass silently
+        pytest.fail("oracle/_ref/libtsref_vpp.so is missing on the GPU box: run __graft_entry__.build() where "
+                    "/root/reference is mounted (the .so travels with the gpurun snapshot)")
     r = R.RefVPP(5)
     yield r
     r.close()
@@ -299,21 +301,70 @@ def test_host_buffer_entry_zero_copy_from_pinned_memory(vp):
         assert _same(o.reshape(-1), _run_oracle(y, uv, kw))
 
 
-def test_aten_handoff_extension_matches_ctypes_path(vp):
-    """csrc/aten_handoff.cpp (the PyTorch C++ extension of the hand-off): same bits
-    as the ctypes path, outputs allocated by torch on torch's current stream."""
-    from tensor_stream_b200 import aten_build, vpp
+def _need_aten():
+    from tensor_stream_b200 import aten_build
     if aten_build.so_path() is None:
-        pytest.skip("_tsvpp_torch.so not built")
+        pytest.fail("_tsvpp_torch.so missing on the GPU box: __graft_entry__.build() must have built it")
+
+
+def test_aten_handoff_extension_matches_oracle(vp):
+    """csrc/aten_handoff.cpp (the PyTorch C++ extension of the hand-off) against the CPU oracle:
+    outputs are at::empty tensors allocated by torch, on torch's current stream."""
+    from tensor_stream_b200 import vpp
+    _need_aten()
     for kw in (SYNTH[0][4], dict(dst=(320, 240), resize_type=G.BICUBIC, fourcc=G.RGB24),
-               dict(crop=(64, 32, 704, 512), fourcc=G.HSV), dict(fourcc=G.UYVY, dst=(320, 240))):
-        frames = [_synthetic(1280, 720, seed=400 + i) for i in range(3)]
+               dict(crop=(64, 32, 704, 512), fourcc=G.HSV), dict(fourcc=G.UYVY, dst=(320, 240)),
+               dict(dst=(640, 360), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)):
+        w, h = (1920, 1080) if kw is SYNTH[0][4] else (1280, 720)
+        frames = [_synthetic(w, h, seed=400 + i) for i in range(3)]
         dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
-        a = vpp.convert_batch_aten(dev, _params(kw))
-        b = vp.convert_batch(dev, _params(kw))
+        outs = vpp.convert_batch_aten(dev, _params(kw))
         torch.cuda.synchronize()
-        for x, y in zip(a, b):
-            assert x.shape == y.shape and x.dtype == y.dtype and torch.equal(x, y)
+        shape, es = vpp.output_shape(w, h, _params(kw))
+        for (y, uv), o in zip(frames, outs):
+            assert tuple(o.shape) == tuple(shape) and o.dtype == (torch.float32 if es == 4 else torch.uint8)
+            want = _mask_undefined(_run_oracle(y, uv, kw), kw, w, h)
+            got = _mask_undefined(o.cpu().numpy().reshape(-1), kw, w, h)
+            assert _same(got, want), _diff_report(got, want)
+
+
+def test_aten_handoff_four_consumers_tensor_lifetime(vp):
+    """The wrapper-shaped consumer of SURVEY.md 8f.1: four threads call the per-frame hand-off the way
+    TensorStream.read() is called (reference src/Wrappers/WrapperPython.cpp:265-350).  The reference keeps every
+    result alive in a `tensors` list and frees it when use_count() drops to 1 (:173-184); here the tensors belong to
+    torch's caching allocator.  Tensors a consumer HOLDS must keep their contents while hundreds of later frames are
+    allocated, converted and dropped around them; every result equals the oracle."""
+    import threading
+    from tensor_stream_b200 import vpp
+    _need_aten()
+    kw = dict(dst=(256, 256), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)
+    fp = _params(kw)
+    frames = [_synthetic(1280, 720, seed=700 + i) for i in range(8)]
+    dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
+    want = [torch.from_numpy(_run_oracle(y, uv, kw).reshape(3, 256, 256).copy()) for y, uv in frames]
+    errors = []
+
+    def consumer(t):
+        try:
+            held = []  # (frame index, tensor) pairs the consumer keeps, like a model input queue
+            for n in range(120):
+                k = (t * 3 + n) % len(dev)
+                out = vpp.convert_frame_aten(dev[k][0], dev[k][1], fp, wait=(n % 3 != 0))
+                if n % 10 == 0:
+                    held.append((k, out))  # stays referenced: must never be recycled under us
+                else:
+                    del out                # dropped at once: its block goes back to the allocator
+            torch.cuda.synchronize()
+            for k, tns in held:
+                if not torch.equal(tns.cpu(), want[k]):
+                    errors.append(("held tensor changed", t, k))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=consumer, args=(t,)) for t in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errors, errors[:5]
 
 
 def test_tensor_stream_converter_read_readme_call(vp):
@@ -493,3 +544,93 @@ def test_prebuilt_batch_handles_every_fourcc(vp):
             want = _mask_undefined(_run_oracle(y, uv, kw), kw, 1280, 720)
             assert _same(got, want), _diff_report(got, want)
         b.destroy()
+
+
+def test_invalid_sizes_are_errors_not_crashes(vp):
+    """Negative / zero sizes reach the C ABI as status codes (ADVICE r1: a std::length_error used to escape
+    through extern "C"; a frame without a chroma row indexed an empty plane)."""
+    from tensor_stream_b200 import vpp
+    y = torch.zeros((64, 64), dtype=torch.uint8, device="cuda")
+    uv = torch.zeros((32, 64), dtype=torch.uint8, device="cuda")
+    for bad in (dict(width=-5, height=16), dict(width=16, height=-1), dict(width=1 << 20, height=16)):
+        with pytest.raises(vpp.VppError):
+            vp.convert(y, uv, vpp.FrameParameters(**bad))
+    with pytest.raises(vpp.VppError):
+        vp.convert(y[:1], uv[:1], vpp.FrameParameters(), width=64, height=1)  # no chroma row
+    out = vp.convert(y, uv, vpp.FrameParameters(16, 16))  # the context still works
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (16, 16, 3)
+
+
+def test_plan_cache_is_bounded(vp):
+    """Per-frame ROI crops must not grow the plan cache without limit (LRU, TSVPP_MAX_PLANS, default 64);
+    evicted plans free their tables only after the launches that use them."""
+    from tensor_stream_b200 import vpp
+    y, uv = _synthetic(640, 360, seed=5)
+    ty, tuv = torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()
+    first = None
+    for k in range(90):
+        fp = vpp.FrameParameters(64, 64, crop_coords=(2 * k, 0, 2 * k + 320, 200), resize_type=vpp.ResizeType.BILINEAR)
+        out = vp.convert(ty, tuv, fp)
+        if k == 0:
+            first = out.clone()
+    torch.cuda.synchronize()
+    assert vp.plan_cache_size() <= 64
+    fp0 = vpp.FrameParameters(64, 64, crop_coords=(0, 0, 320, 200), resize_type=vpp.ResizeType.BILINEAR)
+    again = vp.convert(ty, tuv, fp0)  # its plan was evicted and is rebuilt
+    torch.cuda.synchronize()
+    assert torch.equal(again, first)
+
+
+def test_concurrent_convert_calls_share_the_descriptor_ring(vp):
+    """64 threads x 40 calls through tsvpp_convert_batch on their own streams: more callers than ring slots
+    (kRing = 32) must neither overwrite a descriptor block in flight nor wait on an unrecorded event."""
+    import threading
+    kw = dict(dst=(128, 96), resize_type=G.BILINEAR)
+    frames = [_synthetic(640, 360, seed=40 + i) for i in range(4)]
+    dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
+    want = [_run_oracle(y, uv, kw) for y, uv in frames]
+    errors = []
+
+    def work(t):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for n in range(40):
+                    k = (t + n) % 4
+                    o = vp.convert(dev[k][0], dev[k][1], _params(kw))
+                    st.synchronize()
+                    if o.cpu().numpy().reshape(-1).tobytes() != want[k].tobytes():
+                        errors.append((t, n))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(64)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errors, errors[:5]
+
+
+def test_two_contexts_on_two_gpus_in_one_process():
+    """every entry point binds to its context's device and restores the caller's
+    (reference python_examples/different_streams.py runs one reader per GPU in one process)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from tensor_stream_b200 import vpp
+    kw = dict(dst=(256, 256), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)
+    y, uv = _synthetic(1280, 720, seed=77)
+    want = _run_oracle(y, uv, kw)
+    torch.cuda.set_device(0)
+    v0, v1 = vpp.VideoProcessor(0), vpp.VideoProcessor(1)
+    assert torch.cuda.current_device() == 0
+    for dev, v in ((1, v1), (0, v0), (1, v1)):
+        ty, tuv = torch.from_numpy(y).to("cuda:%d" % dev), torch.from_numpy(uv).to("cuda:%d" % dev)
+        out = torch.empty((3, 256, 256), dtype=torch.float32, device="cuda:%d" % dev)
+        # the caller's current device stays 0 the whole time, also while converting on GPU 1
+        v.convert(ty, tuv, _params(kw), out=out)
+        assert torch.cuda.current_device() == 0
+        torch.cuda.synchronize(dev)
+        assert out.cpu().numpy().reshape(-1).tobytes() == want.tobytes()
+    v1.close()
+    assert torch.cuda.current_device() == 0
+    v0.close()

@@ -28,7 +28,7 @@ def _build():
         pytest.skip("nvcc not available")
     libdir = os.path.dirname(lib)
     subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"), src,
-                           "-o", BIN, "-L", libdir, "-l:libtsvpp.so", "-Xlinker", "-rpath=" + libdir])
+                           "-o", BIN, "-L", libdir, "-l:libtsvpp.so", "-Xlinker", "-rpath=" + libdir, "-Xlinker", "--allow-shlib-undefined"])
     return BIN
 
 
@@ -55,6 +55,18 @@ def test_ring_consumers_bit_exact(env):
     if env.get("TSVPP_COALESCE") != "0":
         stats = [ln for ln in r.stdout.splitlines() if ln.startswith("coalesce_stats")][0].split()
         assert int(stats[2]) == 8 * 96 and int(stats[4]) <= 8 * 96
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"RING_OUT": "pool"}, {"RING_OUT": "pool", "TSVPP_ASYNC": "1"},
+                                 {"RING_OUT": "pool", "TSVPP_ASYNC": "1", "TSVPP_CO_EVENTS": "1"},
+                                 {"RING_OUT": "pool", "TSVPP_ASYNC": "2"}, {"RING_OUT": "pool", "TSVPP_CO_THREAD": "0"}],
+                         ids=["into_sync", "into_async", "into_async_event_fallback", "into_posted", "into_sync_flat_combining"])
+def test_ring_consumers_convert_into_recycled_buffers(env):
+    """VideoProcessor::ConvertInto (caller-owned result buffers, no CUDA call per frame) through the same ring:
+    bit-exact, with completion tickets and with the event fallback."""
+    r = subprocess.run([_build(), "run", "8", "128", "1"], text=True, capture_output=True, env=dict(os.environ, **env))
+    assert r.returncode == 0 and " bad 0 " in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.gpu

@@ -25,7 +25,7 @@ def _build():
         pytest.skip("nvcc not available")
     libdir = os.path.dirname(lib)
     subprocess.check_call(["nvcc", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", BIN,
-                           "-L", libdir, "-l:libtsvpp.so", "-Xlinker", "-rpath=" + libdir])
+                           "-L", libdir, "-l:libtsvpp.so", "-Xlinker", "-rpath=" + libdir, "-Xlinker", "--allow-shlib-undefined"])
     return BIN
 
 
