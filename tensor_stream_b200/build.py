@@ -24,6 +24,13 @@ NVCC_FLAGS = [
 ]
 
 
+# The C++ drop-in (VideoProcessor.cpp) must see the AVFrame its callers see: point TSVPP_FFMPEG_INCLUDE at the FFmpeg
+# headers the wrapper is built with (include/tsvpp_avframe.h; without them a stand-in struct is compiled in and
+# VideoProcessor::Init refuses callers with another layout).
+if os.environ.get("TSVPP_FFMPEG_INCLUDE"):
+    NVCC_FLAGS += ["-I", os.environ["TSVPP_FFMPEG_INCLUDE"], "-DTSVPP_HAVE_FFMPEG"]
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
