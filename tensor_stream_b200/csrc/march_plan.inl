@@ -106,8 +106,9 @@ static bool find_div_magic(unsigned D, unsigned long long nmax, unsigned *mul, i
 
 static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) {
     (void)sm_count;
-    const bool bicubic = in.rs == RS_BICUBIC;
-    if (!bicubic && in.rs != RS_AREA) return TSVPP_UNSUPPORTED;
+    const bool bicubic = in.rs == RS_BICUBIC, bilinear = in.rs == RS_BILINEAR;
+    if (!bicubic && !bilinear && in.rs != RS_AREA) return TSVPP_UNSUPPORTED;
+    const int BW = bilinear ? 4 : 2;  // output columns per consumer thread (march_bw)
     const int dw = in.dw, dh = in.dh, H = in.H;
     const Geometry &g = in.g;
     const bool need_uv = in.need_uv;
@@ -117,7 +118,25 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     bool xlong = false, ylong = false;
     std::vector<int> pxi, pyi;  // area integer patterns
     int NW = 1;
-    if (bicubic) {
+    std::vector<int> bmx, bmy;  // bilinear: weights of the second tap, m / 2^ex and m / 2^ey
+    if (bilinear) {
+        std::vector<double> vx(dw), vy(dh);
+        for (int j = 0; j < dw; ++j) vx[j] = (*in.xs)[j].w;
+        for (int i = 0; i < dh; ++i) vy[i] = (*in.ys)[i].w;
+        ex = dyadic_q(vx.data(), vx.size(), 7);
+        ey = dyadic_q(vy.data(), vy.size(), 7);
+        if (ex < 0 || ey < 0) return TSVPP_UNSUPPORTED;  // 8 + ex + ey <= 22 bits: every f32 product and sum is exact
+        bmx.resize(dw);
+        bmy.resize(dh);
+        for (int j = 0; j < dw; ++j) {
+            bmx[j] = (int)std::ldexp(vx[j], ex);
+            if (bmx[j] < 0 || bmx[j] > (1 << ex)) return TSVPP_UNSUPPORTED;
+        }
+        for (int i = 0; i < dh; ++i) {
+            bmy[i] = (int)std::ldexp(vy[i], ey);
+            if (bmy[i] < 0 || bmy[i] > (1 << ey)) return TSVPP_UNSUPPORTED;
+        }
+    } else if (bicubic) {
         qx = dyadic_q(in.cxw->data(), (size_t)4 * dw, 27, kDyadicTol);
         qy = dyadic_q(in.cyw->data(), (size_t)4 * dh, 27, kDyadicTol);
         if (qx < 0 || qy < 0) return TSVPP_UNSUPPORTED;
@@ -150,7 +169,11 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     auto luma_rows_of = [&](int i, int rows[64]) -> int {  // source rows of output luma row i, clamped like build_plan
         const AxisSample &s = (*in.ys)[i];
         int n = 0;
-        if (bicubic) {
+        if (bilinear) {
+            int t[2];
+            bilinear_taps(s.pos, 1, g.sh, t);
+            for (int k = 0; k < 2; ++k) rows[n++] = std::max(0, std::min(g.y0 + t[k], H - 1));
+        } else if (bicubic) {
             int t[4];
             bicubic_taps(s.pos, 1, g.sh, t);
             for (int k = 0; k < 4; ++k) rows[n++] = std::max(0, std::min(g.y0 + t[k], H - 1));
@@ -164,7 +187,11 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     auto chroma_rows_of = [&](int ci, int rows[64]) -> int {
         const AxisSample &s = (*in.ys)[std::min(ci, dh - 1)];  // luma-grid formula at the chroma index
         int n = 0;
-        if (bicubic) {
+        if (bilinear) {
+            int t[2];
+            bilinear_taps(s.pos, 1, g.sh / 2, t);
+            for (int k = 0; k < 2; ++k) rows[n++] = std::max(0, std::min(g.y0 / 2 + t[k], H / 2 - 1));
+        } else if (bicubic) {
             int t[4];
             bicubic_taps(s.pos, 1, g.sh / 2, t);
             for (int k = 0; k < 4; ++k) rows[n++] = std::max(0, std::min(g.y0 / 2 + t[k], H / 2 - 1));
@@ -209,8 +236,8 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     };
 
     // per-column window geometry relative to the tile segment start, for a candidate tile width
-    const int lwords = bicubic ? 2 : NW + 1;      // 32-bit words a luma column reads per row
-    const int cwords = bicubic ? 3 : 2 * NW + 1;  // words a chroma pair reads per row
+    const int lwords = bilinear ? 2 : bicubic ? 2 : NW + 1;      // 32-bit words a luma column reads per row
+    const int cwords = bilinear ? 2 : bicubic ? 3 : 2 * NW + 1;  // words a chroma pair reads per row
     struct Tiles {
         std::vector<int> a0l, lenl, a0c, lenc;
         int stride = 16, nt = 1;
@@ -271,7 +298,7 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
                 if (want_rpg && crpg != want_rpg) continue;
                 for (int cG = 8; cG >= 1; cG >>= 1) {
                     if (want_g && cG != want_g) continue;
-                    const int cons = (ctw / 2) * cG;
+                    const int cons = (ctw / BW) * cG;
                     if (cons > kMarchMaxThreads - 32) continue;
                     const int R = 2 * cG * crpg;
                     if (R > 2 && R >= 2 * round_up(dh, 2)) continue;  // don't over-size strips for short outputs
@@ -288,6 +315,10 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
                         const int ctas = std::max(1, std::min(std::min(by_smem, by_regs), 2048 / threads));
                         // useful fraction of the marched rows: a group restarts its window (3 extra source rows)
                         double eff = 1.0;
+                        if (bilinear) {
+                            const double rows_ideal = 2.0 * crpg * (double)g.sh / dh;
+                            eff = rows_ideal / (rows_ideal + 1.0);
+                        }
                         if (bicubic) {
                             const double rows_ideal = 2.0 * crpg * std::max(1.0, (double)g.sh / dh);
                             eff = rows_ideal / (rows_ideal + 3.0);
@@ -320,7 +351,63 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     DeviceArena ar;
     size_t off_row_l = 0, off_row_c = 0, off_gfl = 0, off_gfc = 0;
     int rows[64];
-    if (bicubic) {
+    if (bilinear) {
+        std::vector<MarchRowL> rl((size_t)nstrips * R, MarchRowL{0, 0, 0, 0}), rc((size_t)std::max(1, nstrips * (R / 2)), MarchRowL{0, 0, 0, 0});
+        std::vector<int> gfl((size_t)nstrips * G, 0), gfc((size_t)nstrips * G, 0);
+        // the two-row window {marched - 1, marched}; taps are folded onto it like the bicubic ones (the bottom
+        // border pulls a row's taps back: yDiff = 0, src/Resize.cu:9-10)
+        auto fill_row = [&](MarchRowL &r, const std::vector<int> &list, const int *srows, int my, int &marched, int *first_out) -> bool {
+            const int s0 = slot_of(list, srows[0]), s1 = slot_of(list, srows[1]);
+            marched = std::max(marched, std::max(s0, s1));
+            if (marched - std::min(s0, s1) > 1) return false;
+            int w[2] = {0, 0};  // [0] = slot marched - 1, [1] = slot marched
+            w[1 - (marched - s0)] += (1 << ey) - my;
+            w[1 - (marched - s1)] += my;
+            if (first_out) *first_out = std::min(s0, s1);
+            r.marched = marched;
+            r.w_old = w[0];
+            r.w_new = w[1];
+            return true;
+        };
+        for (int st = 0; st < nstrips; ++st) {
+            int last_valid = -1, marched = -1;
+            for (int k = 0; k < R; ++k) {
+                const int i = st * R + k;
+                const bool gstart = k % (2 * rpg) == 0;
+                if (gstart) marched = -1;
+                if (i < dh) {
+                    luma_rows_of(i, rows);
+                    if (!fill_row(rl[i], SL.l[st], rows, bmy[i], marched, gstart ? &gfl[(size_t)st * G + k / (2 * rpg)] : nullptr))
+                        return TSVPP_UNSUPPORTED;
+                    last_valid = i;
+                } else {
+                    rl[i] = rl[last_valid];
+                }
+            }
+            if (need_uv) {
+                last_valid = -1;
+                marched = -1;
+                for (int k = 0; k < R / 2; ++k) {
+                    const int ci = st * (R / 2) + k;
+                    const bool gstart = k % rpg == 0;
+                    if (gstart) marched = -1;
+                    if (ci < in.ch2) {
+                        chroma_rows_of(ci, rows);
+                        // the chroma row is weighted like luma row index ci (same x, y, wx, wy: src/Resize.cu:303-310)
+                        if (!fill_row(rc[ci], SL.c[st], rows, bmy[std::min(ci, dh - 1)], marched, gstart ? &gfc[(size_t)st * G + k / rpg] : nullptr))
+                            return TSVPP_UNSUPPORTED;
+                        last_valid = ci;
+                    } else if (last_valid >= 0) {
+                        rc[ci] = rc[last_valid];
+                    }
+                }
+            }
+        }
+        off_row_l = ar.add(rl.data(), rl.size() * sizeof(MarchRowL));
+        off_row_c = ar.add(rc.data(), rc.size() * sizeof(MarchRowL));
+        off_gfl = ar.add(gfl.data(), gfl.size() * sizeof(int));
+        off_gfc = ar.add(gfc.data(), gfc.size() * sizeof(int));
+    } else if (bicubic) {
         std::vector<MarchRowB> rl((size_t)nstrips * R), rc((size_t)std::max(1, nstrips * (R / 2)));
         std::memset(rl.data(), 0, rl.size() * sizeof(MarchRowB));
         std::memset(rc.data(), 0, rc.size() * sizeof(MarchRowB));
@@ -423,7 +510,39 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     // ---------------- column tables ----------------
     const int ncol = ntiles * tw;
     size_t off_col_l = 0, off_col_c = 0, off_pxw = 0, off_pyw = 0, off_dmul = 0, off_dsh = 0;
-    if (bicubic) {
+    if (bilinear) {
+        std::vector<MarchColL> cl(ncol, MarchColL{0, 0x3210u, 0x3210u, 0}), cc(ncol / 2 + 2, MarchColL{0, 0x3210u, 0x3210u, 0});
+        auto weights = [&](int mx, bool same) -> unsigned {
+            // taps that coincide (right border, xDiff = 0) carry the whole weight on byte 0
+            return same ? (unsigned)(1 << ex) : ((unsigned)((1 << ex) - mx) | ((unsigned)mx << 8));
+        };
+        for (int j = 0; j < dw; ++j) {
+            const int t = j / tw;
+            const int o0 = (*in.tap_l)[(size_t)j * 4] - TL.a0l[t], o1 = (*in.tap_l)[(size_t)j * 4 + 1] - TL.a0l[t];
+            if (o0 < 0 || o1 < o0) return TSVPP_UNSUPPORTED;
+            const int base = o0 & ~3;
+            if (o1 - base > 7) return TSVPP_UNSUPPORTED;
+            cl[j].addr = base;
+            cl[j].sel0 = (unsigned)(o0 - base) | ((unsigned)(o1 - base) << 4) | 0x3200u;
+            cl[j].w = weights(bmx[j], o1 == o0);
+        }
+        if (need_uv)
+            for (int cj = 0; cj < in.cw2; ++cj) {
+                const int j = 2 * cj, t = j / tw;
+                const int u0 = (*in.tap_c)[(size_t)j * 4] - TL.a0c[t], u1 = (*in.tap_c)[(size_t)j * 4 + 1] - TL.a0c[t];
+                const int v0 = (*in.tap_c)[(size_t)(j + 1) * 4] - TL.a0c[t], v1 = (*in.tap_c)[(size_t)(j + 1) * 4 + 1] - TL.a0c[t];
+                if (u0 < 0 || u1 < u0 || v0 < u0 || v1 < v0) return TSVPP_UNSUPPORTED;
+                const int base = u0 & ~3;
+                if (v1 - base > 7 || u1 - base > 7) return TSVPP_UNSUPPORTED;
+                if ((u1 == u0) != (v1 == v0)) return TSVPP_UNSUPPORTED;
+                cc[cj].addr = base;
+                cc[cj].sel0 = (unsigned)(u0 - base) | ((unsigned)(u1 - base) << 4) | 0x3200u;
+                cc[cj].sel1 = (unsigned)(v0 - base) | ((unsigned)(v1 - base) << 4) | 0x3200u;
+                cc[cj].w = weights(bmx[cj], u1 == u0);  // the pair is weighted like luma column cj
+            }
+        off_col_l = ar.add(cl.data(), cl.size() * sizeof(MarchColL));
+        off_col_c = ar.add(cc.data(), cc.size() * sizeof(MarchColL));
+    } else if (bicubic) {
         MarchColB z;
         std::memset(&z, 0, sizeof(z));
         z.sel0 = 0x3210u;
@@ -566,7 +685,8 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     MarchPlanDev &D = out.dev;
     std::memset(&D, 0, sizeof(D));
     D.e.dw = dw; D.e.dh = dh; D.e.cw2 = in.cw2; D.e.ch2 = in.ch2; D.e.swap_rb = in.swap_rb; D.e.need_uv = need_uv ? 1 : 0;
-    D.mode = bicubic ? MARCH_BICUBIC : MARCH_AREA;
+    D.mode = bilinear ? MARCH_BILINEAR : bicubic ? MARCH_BICUBIC : MARCH_AREA;
+    D.vshift = ex + ey;
     D.tw = tw; D.ntiles = ntiles; D.nstrips = nstrips; D.G = G; D.rpg = rpg;
     D.nsl = nsl; D.nsc = nsc; D.slot_stride = slot_stride;
     D.stage_bytes = (nsl + nsc) * slot_stride;
@@ -597,10 +717,10 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     out.fetch_bytes_per_frame = fetch;
     char buf[640];
     std::snprintf(buf, sizeof(buf),
-                  "kernel=march resample=%s-int out_kind=%d fill=bulk bw=2 tw=%d G=%d rpg=%d strip_rows=%d ntiles=%d nstrips=%d "
+                  "kernel=march resample=%s-int out_kind=%d fill=bulk bw=%d tw=%d G=%d rpg=%d strip_rows=%d ntiles=%d nstrips=%d "
                   "slots=%d+%d slot_stride=%d stage_bytes=%d nstages=%d smem=%zu threads=%d ctas_per_sm=%d qx=%d qy=%d "
                   "digits=%s/%s K=%d KX=%d NW=%d PX=%d PY=%d crop=%d resize=1 fetch_bytes_per_frame=%ld direct=0",
-                  bicubic ? "bicubic" : "area", in.ok, tw, G, rpg, R, ntiles, nstrips, nsl, nsc, slot_stride, D.stage_bytes,
+                  bilinear ? "bilinear" : bicubic ? "bicubic" : "area", in.ok, BW, tw, G, rpg, R, ntiles, nstrips, nsl, nsc, slot_stride, D.stage_bytes,
                   nstages, out.smem, out.threads, out.ctas_per_sm, bicubic ? qx : ex, bicubic ? qy : ey,
                   xlong ? "long" : "short", ylong ? "long" : "short", K, in.KX, NW, in.PX, in.PY, (int)g.crop, fetch);
     out.desc = buf;

@@ -911,7 +911,11 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
                   rs_names[rs], ok, bulk ? "bulk" : "ldg", bw, tw, rp, K, KX, ntiles, nstrips, slot_stride, D.stage_bytes,
                   nstages, pl->smem, fused_block_threads(D), pl->ctas_per_sm, (int)g.crop, (int)g.resize, fetch, D.direct);
     pl->desc = buf;
-    if (bulk && (rs == RS_BICUBIC || rs == RS_AREA) && !ctx->no_march) {
+    // bilinear goes through the integer kernel where its 4-column blocks and once-per-row staging pay: wide outputs
+    // that are not strong downscales (upscales, mild downscales); TSVPP_MARCH_BILINEAR=1/0 forces / forbids it
+    const int mb = env_int("TSVPP_MARCH_BILINEAR", -1);
+    const bool march_bilinear = rs == RS_BILINEAR && (mb == 1 || (mb != 0 && dw >= 512 && dw % 4 == 0 && xr <= 2.0f && yr <= 2.0f));
+    if (bulk && (rs == RS_BICUBIC || rs == RS_AREA || march_bilinear) && !ctx->no_march) {
         MarchInputs mi;
         mi.g = g; mi.rs = rs; mi.ok = ok; mi.need_uv = need_uv;
         mi.W = W; mi.H = H; mi.pitch_y = pitch_y; mi.pitch_uv = pitch_uv;
@@ -930,7 +934,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
             pl->march_smem = mh.smem;
             pl->march_ctas_per_sm = cap_ctas > 0 ? std::min(mh.ctas_per_sm, cap_ctas) : mh.ctas_per_sm;
             pl->fetch_bytes_per_frame = mh.fetch_bytes_per_frame;
-            pl->vec_ok_geom = (dw % 2 == 0) ? 1 : 0;
+            pl->vec_ok_geom = (dw % march_bw(mh.dev.mode) == 0) ? 1 : 0;
             pl->desc = mh.desc;
         } else {
             if (mh.dev_tables) cudaFree(mh.dev_tables);

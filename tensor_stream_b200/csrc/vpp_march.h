@@ -27,7 +27,13 @@
 
 namespace tsvpp {
 
-enum MarchMode : int { MARCH_BICUBIC = 0, MARCH_AREA = 1 };
+enum MarchMode : int { MARCH_BICUBIC = 0, MARCH_AREA = 1, MARCH_BILINEAR = 2 };
+
+// output columns per consumer thread: bilinear 4 (12-byte / float4 row stores), the others 2
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int march_bw(int mode) { return mode == MARCH_BILINEAR ? 4 : 2; }
 
 #ifndef TSVPP_MARCH_MAXTHREADS
 #define TSVPP_MARCH_MAXTHREADS 288
@@ -60,6 +66,21 @@ struct MarchRowB {
     int w[4];       // vertical weight digits folded onto the window bytes (w[0..1] sit in the first 16 bytes)
     int pad1[2];
 };
+// bilinear (also AREA when it is not a strict downscale, reference src/Resize.cu:214-240): the horizontal two-tap sum
+// is kept UNROUNDED (A*(2^ex - mx) + B*mx < 2^15), the vertical one is shifted once at the end -- the reference
+// truncates a single exact f32 expression (src/Resize.cu:5-25), so there is no intermediate rounding to mirror.
+struct MarchColL {  // one luma column, or one chroma pair
+    int addr;       // byte offset (multiple of 4) of the first of the two words the taps lie in
+    unsigned sel0;  // luma: PRMT selector putting tap 0 / tap 1 into bytes 0 / 1.  chroma: the same for U
+    unsigned sel1;  // chroma: for V
+    unsigned w;     // byte 0 = weight of tap 0 (2^ex - mx, or 2^ex when the taps coincide), byte 1 = weight of tap 1
+};
+struct MarchRowL {
+    int marched;  // strip-relative slot the two-row window must have been marched to
+    int w_old;    // weight of the older row of the window (0 .. 2^ey)
+    int w_new;    // weight of the newest row
+    int pad;
+};
 // area: per output row
 struct MarchRowA {
     int first;  // strip-relative slot of the first window row
@@ -75,6 +96,7 @@ struct MarchPlanDev {
     int slot_stride, stage_bytes, nstages;
     int pitch_y, pitch_uv;
     int need_uv;
+    int vshift;              // bilinear: ex + ey
     // bicubic
     int xlong, ylong;        // weight digits: 0 = short (q <= 13), 1 = long
     int qx, qy;              // weights are m / 2^q

@@ -24,6 +24,9 @@
 #ifndef TSVPP_MARCH_MINBLOCKS_BICUBIC
 #define TSVPP_MARCH_MINBLOCKS_BICUBIC 3
 #endif
+#ifndef TSVPP_MARCH_MINBLOCKS_BILINEAR
+#define TSVPP_MARCH_MINBLOCKS_BILINEAR 2
+#endif
 #ifndef TSVPP_MARCH_MINBLOCKS_AREA
 #define TSVPP_MARCH_MINBLOCKS_AREA 2
 #endif
@@ -362,12 +365,89 @@ __device__ __forceinline__ void march_bicubic_group(const MarchPlanDev &P, const
 }
 
 // ---------------------------------------------------------------------------------------
+// bilinear: one thread, FOUR output columns (two chroma pairs), the rpg row pairs of its row group
+// ---------------------------------------------------------------------------------------
+struct BilinearCols {
+    int addr[4], caddr[2];
+    uint32_t sel[4], w[4], selu[2], selv[2], cw[2];
+};
+
+// reference src/Resize.cu:5-25 with exact dyadic weights: (int)v = (H_old * w_old + H_new * w_new) >> (ex + ey) with
+// H = A * (2^ex - mx) + B * mx per source row.  Nothing rounds before the final truncation, values stay in [0, 255].
+template <int OK, bool NEED_UV>
+__device__ __forceinline__ void march_bilinear_group(const MarchPlanDev &P, const BilinearCols &lc, uint32_t stage,
+                                                     uint32_t stage_c, uint32_t sstride, int strip, int g, int j0, bool vec,
+                                                     void *outp) {
+    const int R2 = P.G * P.rpg;
+    const int pr0 = strip * R2 + g * P.rpg;
+    const MarchRowL *rowl = reinterpret_cast<const MarchRowL *>(P.row_l);
+    const MarchRowL *rowc = reinterpret_cast<const MarchRowL *>(P.row_c);
+    const int dh = P.e.dh, ch2 = P.e.ch2, rpg = P.rpg, vsh = P.vshift;
+    uint32_t H0[4] = {0, 0, 0, 0}, H1[4] = {0, 0, 0, 0};
+    uint32_t U0[2] = {0, 0}, U1[2] = {0, 0}, V0[2] = {0, 0}, V1[2] = {0, 0};
+    int curl = __ldg(P.gfirst_l + strip * P.G + g) - 1;
+    int curc = NEED_UV ? __ldg(P.gfirst_c + strip * P.G + g) - 1 : 0;
+    uint32_t sl_l = stage + (uint32_t)(curl + 1) * sstride;
+    uint32_t sl_c = stage_c + (uint32_t)(curc + 1) * sstride;
+    for (int p = 0; p < rpg; ++p) {
+        const int pr = pr0 + p;
+        const int i0 = 2 * pr;
+        if (i0 >= dh) break;
+        const int4 ra = __ldg(reinterpret_cast<const int4 *>(rowl + i0));
+        const int4 rb = __ldg(reinterpret_cast<const int4 *>(rowl + i0 + 1));
+        int4 rc = make_int4(0, 0, 0, 0);
+        if (NEED_UV) rc = __ldg(reinterpret_cast<const int4 *>(rowc + pr));
+        int Yv[2][4];
+        int UV[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int4 r = a ? rb : ra;
+            for (int n = r.x - curl; n > 0; --n, ++curl, sl_l += sstride) {  // uniform
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t t = __byte_perm(lds32(sl_l + lc.addr[c]), lds32(sl_l + lc.addr[c] + 4), lc.sel[c]);
+                    H0[c] = H1[c];
+                    H1[c] = dp4a_uu(t, lc.w[c], 0u);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Yv[a][c] = (int)((H0[c] * (uint32_t)r.y + H1[c] * (uint32_t)r.z) >> vsh);
+        }
+        if (NEED_UV && pr < ch2) {
+            for (int n = rc.x - curc; n > 0; --n, ++curc, sl_c += sstride) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t x0 = lds32(sl_c + lc.caddr[c]), x1 = lds32(sl_c + lc.caddr[c] + 4);
+                    U0[c] = U1[c];
+                    V0[c] = V1[c];
+                    U1[c] = dp4a_uu(__byte_perm(x0, x1, lc.selu[c]), lc.cw[c], 0u);
+                    V1[c] = dp4a_uu(__byte_perm(x0, x1, lc.selv[c]), lc.cw[c], 0u);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if ((j0 >> 1) + c < P.e.cw2) {
+                    UV[c][0] = (int)((U0[c] * (uint32_t)rc.y + U1[c] * (uint32_t)rc.z) >> vsh);
+                    UV[c][1] = (int)((V0[c] * (uint32_t)rc.y + V1[c] * (uint32_t)rc.z) >> vsh);
+                }
+        }
+        const int nx = min(4, P.e.dw - j0), ny = min(2, dh - i0);
+        if (nx > 0) {
+            if (nx == 4 && ny == 2 && vec)
+                emit_block<OK, 4>(P.e, outp, i0, j0, Yv, UV, 4, 2, true);
+            else
+                emit_block<OK, 4>(P.e, outp, i0, j0, Yv, UV, nx, ny, false);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
 // MODE: MARCH_BICUBIC / MARCH_AREA.  VAR: bicubic: bit 0 = long horizontal digits, bit 1 = long vertical digits;
 // area: NW (1, 2 or 4).
 template <int MODE, int VAR, int OK>
-__global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVPP_MARCH_MINBLOCKS_BICUBIC : TSVPP_MARCH_MINBLOCKS_AREA)
+__global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVPP_MARCH_MINBLOCKS_BICUBIC : MODE == MARCH_BILINEAR ? TSVPP_MARCH_MINBLOCKS_BILINEAR : TSVPP_MARCH_MINBLOCKS_AREA)
     vpp_march_kernel(const MarchPlanDev P, const FrameDev *__restrict__ frames, int nframes, int vec_ok) {
     constexpr bool NEED_UV = !(OK == OUT_Y800_U8 || OK == OUT_Y800_F32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -411,7 +491,8 @@ __global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVP
 
     // ================= consumers =================
     const int ctid = tid - 32;
-    const int blocks_x = P.tw >> 1;
+    constexpr int BW = march_bw(MODE);
+    const int blocks_x = P.tw / BW;
     const int tx = ctid % blocks_x;  // column block inside the tile
     const int g = ctid / blocks_x;   // row group inside the strip
     const bool active = g < P.G;
@@ -423,6 +504,7 @@ __global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVP
     int cur_tile = -1;
     // per-tile column state
     BicubicCols<(MODE == MARCH_BICUBIC) && ((VAR & 1) != 0)> bc;
+    BilinearCols lc;
     int a_addr0 = 0, a_addr1 = 0, a_addrc = 0, a_sh0 = 0, a_sh1 = 0, a_shc = 0, a_pr0 = 0, a_pr1 = 0, a_prc = 0;
     constexpr int NW = (MODE == MARCH_AREA) ? VAR : 1;
     uint32_t a_w0[NW], a_w1[NW], a_wc[NW];
@@ -434,12 +516,27 @@ __global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVP
     for (int it = 0; it < my_items; ++it, ic.next(P)) {
         const uint32_t stage = sbase + (uint32_t)(s * P.stage_bytes);
         const uint32_t stage_c = stage + (uint32_t)P.nsl * sstride;
-        const int j0 = ic.tile * P.tw + 2 * tx;
+        const int j0 = ic.tile * P.tw + BW * tx;
         const bool have_c = NEED_UV && (j0 >> 1) < P.e.cw2;
         if (active && ic.tile != cur_tile) {
             cur_tile = ic.tile;
-            const int cidx = ic.tile * P.tw + 2 * tx;  // tables are padded to ntiles*tw columns
-            if constexpr (MODE == MARCH_BICUBIC) {
+            const int cidx = ic.tile * P.tw + BW * tx;  // tables are padded to ntiles*tw columns
+            if constexpr (MODE == MARCH_BILINEAR) {
+                const MarchColL *cl = reinterpret_cast<const MarchColL *>(P.col_l) + cidx;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int4 v = __ldg(reinterpret_cast<const int4 *>(cl + c));
+                    lc.addr[c] = v.x; lc.sel[c] = (uint32_t)v.y; lc.w[c] = (uint32_t)v.w;
+                }
+                if (NEED_UV) {
+                    const MarchColL *cc = reinterpret_cast<const MarchColL *>(P.col_c) + (cidx >> 1);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int4 v = __ldg(reinterpret_cast<const int4 *>(cc + c));
+                        lc.caddr[c] = v.x; lc.selu[c] = (uint32_t)v.y; lc.selv[c] = (uint32_t)v.z; lc.cw[c] = (uint32_t)v.w;
+                    }
+                }
+            } else if constexpr (MODE == MARCH_BICUBIC) {
                 const MarchColB *cl = reinterpret_cast<const MarchColB *>(P.col_l) + cidx;
                 const MarchColB *cc = NEED_UV ? reinterpret_cast<const MarchColB *>(P.col_c) + (cidx >> 1) : nullptr;
                 bc.load(cl, cc);
@@ -467,7 +564,9 @@ __global__ void __launch_bounds__(kMarchMaxThreads, MODE == MARCH_BICUBIC ? TSVP
 
         if (active) {
             void *outp = frames[ic.frame].out;
-            if constexpr (MODE == MARCH_BICUBIC) {
+            if constexpr (MODE == MARCH_BILINEAR) {
+                march_bilinear_group<OK, NEED_UV>(P, lc, stage, stage_c, sstride, ic.strip, g, j0, vec, outp);
+            } else if constexpr (MODE == MARCH_BICUBIC) {
                 march_bicubic_group<(VAR & 1) != 0, (VAR & 2) != 0, OK, NEED_UV>(P, bc, stage, stage_c, sstride, ic.strip, g, j0,
                                                                                   have_c, vec, outp);
             } else {
@@ -577,6 +676,7 @@ static MarchFn pick_ok(int ok) {
     return nullptr;
 }
 static MarchFn pick_march(const MarchPlanDev &P, int ok) {
+    if (P.mode == MARCH_BILINEAR) return pick_ok<MARCH_BILINEAR, 0>(ok);
     if (P.mode == MARCH_BICUBIC) {
         switch ((P.xlong ? 1 : 0) | (P.ylong ? 2 : 0)) {
             case 0: return pick_ok<MARCH_BICUBIC, 0>(ok);
@@ -594,7 +694,7 @@ static MarchFn pick_march(const MarchPlanDev &P, int ok) {
 }
 
 int march_block_threads(const MarchPlanDev &P) {
-    const int cons = (P.tw / 2) * P.G;
+    const int cons = (P.tw / march_bw(P.mode)) * P.G;
     return 32 + (cons + 31) / 32 * 32;
 }
 size_t march_smem_bytes(const MarchPlanDev &P) { return (size_t)P.nstages * P.stage_bytes + 2 * 8 * kMaxStages + 128; }

@@ -60,7 +60,11 @@ SELECT = [
     (1920, 1080, dict(dst=(1024, 1024), resize_type=G.AREA), "NW=1"),
     (1920, 1080, dict(dst=(224, 224), resize_type=G.BICUBIC), None),   # 1920/224 is not dyadic
     (1920, 1080, dict(dst=(299, 299), resize_type=G.AREA), None),
-    (1920, 1080, dict(dst=(256, 256), resize_type=G.BILINEAR), None),
+    (1920, 1080, dict(dst=(256, 256), resize_type=G.BILINEAR), None),   # strong downscale: the float kernel skips rows
+    (1920, 1080, dict(dst=(3840, 2160), resize_type=G.BILINEAR), "resample=bilinear-int"),
+    (1920, 1080, dict(dst=(1280, 720), resize_type=G.BILINEAR), "resample=bilinear-int"),
+    (960, 540, dict(dst=(1920, 1080), resize_type=G.AREA), "resample=bilinear-int"),   # AREA upscale = bilinear arithmetic
+    (1920, 1080, dict(dst=(2500, 1400), resize_type=G.BILINEAR), None),  # 1920/2500 is not dyadic
 ]
 
 
@@ -79,7 +83,8 @@ FORMATS = [(G.RGB24, G.MERGED, False), (G.RGB24, G.MERGED, True), (G.BGR24, G.PL
 
 
 @pytest.mark.parametrize("fourcc,planes,norm", FORMATS, ids=["%s_%s_%s" % (f, p, "f32" if n else "u8") for f, p, n in FORMATS])
-@pytest.mark.parametrize("rt,dst", [(G.BICUBIC, (640, 480)), (G.AREA, (320, 180))], ids=["bicubic_1.5x", "area_4x"])
+@pytest.mark.parametrize("rt,dst", [(G.BICUBIC, (640, 480)), (G.AREA, (320, 180)), (G.BILINEAR, (1920, 1440))],
+                         ids=["bicubic_1.5x", "area_4x", "bilinear_2x_up"])
 def test_every_output_format(vp, rt, dst, fourcc, planes, norm):
     w, h = 960, 720
     if rt == G.AREA:
@@ -109,6 +114,16 @@ GEOM = [
     ("bicubic_narrow_tall", 64, 2048, 64, dict(dst=(32, 1024), resize_type=G.BICUBIC)),
     ("bicubic_wide_short", 4096, 32, 4096, dict(dst=(2048, 16), resize_type=G.BICUBIC, fourcc=G.Y800)),
     ("bicubic_8k_to_4k", 7680, 4320, 7680, dict(dst=(3840, 2160), resize_type=G.BICUBIC, fourcc=G.Y800)),
+    ("bilinear_2x_up", 960, 540, 960, dict(dst=(1920, 1080), resize_type=G.BILINEAR)),
+    ("bilinear_4x_up_pitch", 480, 270, 512, dict(dst=(1920, 1080), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
+    ("bilinear_1.5x_down", 1920, 1080, 1920, dict(dst=(1280, 720), resize_type=G.BILINEAR)),
+    ("bilinear_1.33x_up_x_2x_down_y", 1536, 1440, 1536, dict(dst=(2048, 720), resize_type=G.BILINEAR)),
+    ("bilinear_crop_odd_origin", 1920, 1080, 1920, dict(crop=(33, 17, 33 + 640, 17 + 360), dst=(1280, 720), resize_type=G.BILINEAR)),
+    ("bilinear_crop_bottom_right", 1920, 1080, 1920, dict(crop=(1280, 720, 1920, 1080), dst=(1280, 720), resize_type=G.BILINEAR)),
+    ("bilinear_tall", 32, 512, 32, dict(dst=(512, 1024), resize_type=G.BILINEAR, fourcc=G.HSV)),
+    ("area_upscale_2x", 960, 540, 960, dict(dst=(1920, 1080), resize_type=G.AREA)),
+    ("area_upscale_mixed", 1920, 540, 1920, dict(dst=(960, 1080), resize_type=G.AREA)),
+    ("bilinear_8k_out", 3840, 2160, 3840, dict(dst=(7680, 4320), resize_type=G.BILINEAR, fourcc=G.Y800)),
     ("area_2x", 1920, 1080, 1920, dict(dst=(960, 540), resize_type=G.AREA)),
     ("area_7.5x_by_4.2x", 1920, 1080, 1920, dict(dst=(256, 256), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
     ("area_15x_by_8.4x", 1920, 1080, 2048, dict(dst=(128, 128), resize_type=G.AREA)),
