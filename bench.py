@@ -226,6 +226,8 @@ EXTRAS = [
     ("sweep area 1080p -> BGR24 planar 256x256 f32", (1920, 1080), None, (256, 256), "AREA", "BGR24", "PLANAR", True, 256),
     ("sweep area 1080p -> BGR24 planar 128x128 f32", (1920, 1080), None, (128, 128), "AREA", "BGR24", "PLANAR", True, 256),
     ("no resize 1080p -> RGB24 merged u8 (default read())", (1920, 1080), None, (0, 0), "NEAREST", "RGB24", "MERGED", False, 160),
+    ("no resize 1080p -> UYVY u8", (1920, 1080), None, (0, 0), "NEAREST", "UYVY", "MERGED", False, 160),
+    ("sweep bilinear 1080p -> BGR24 planar 3840x2160 f32", (1920, 1080), None, (3840, 2160), "BILINEAR", "BGR24", "PLANAR", True, 48),
 ]
 
 
@@ -255,7 +257,10 @@ def run_extras(torch, vpp, v, dev, pool1080, barrier, max_over_ranks, world, pea
             shape, es = vpp.output_shape(sw, sh, fp)
             outs = [torch.empty(shape, dtype=torch.float32 if es == 4 else torch.uint8, device=dev) for _ in range(nf)]
             batch = v.make_batch(list(zip(ys[:nf], uvs[:nf])), fp, outs)
-            plan = v.describe_plan(ys[0], uvs[0], fp)
+            try:
+                plan = v.describe_plan(ys[0], uvs[0], fp)
+            except vpp.VppError:
+                plan = "packed YUV kernels (no fused plan)"
             for _ in range(3):
                 batch.run(stream)
             barrier()
@@ -457,6 +462,49 @@ def run_ours(args):
 
     e2e_zc_ms, e2e_st_ms = S.max_over_ranks(
         [e2e_runs["zero_copy"][0] * 1e3, e2e_runs["staged_h2d"][0] * 1e3], device=dev)
+
+    # What the host side of this rank can deliver at all: plain pinned-memory copies, every rank at the same time
+    # (they share the sockets' memory controllers and PCIe root ports).  The end-to-end path is bounded by these,
+    # not by the kernel: compare e2e.pcie_*_gbs_per_gpu with e2e.link.* (H2D alone, D2H alone, both directions at once).
+    link = {}
+    try:
+        nb = 256 << 20
+        hsrc = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        hdst = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+        dbuf2 = torch.empty(nb, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def timed(fn, reps=4):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return reps * nb / (time.perf_counter() - t0) / 1e9
+
+        def h2d():
+            with torch.cuda.stream(s1):
+                dbuf.copy_(hsrc, non_blocking=True)
+
+        def d2h():
+            with torch.cuda.stream(s2):
+                hdst.copy_(dbuf2, non_blocking=True)
+
+        def both():
+            h2d()
+            d2h()
+
+        g_h2d, g_d2h, g_both = timed(h2d), timed(d2h), timed(both)
+        # slowest rank decides: MAX over ranks of the time = MIN of the rates
+        inv = S.max_over_ranks([1.0 / g_h2d, 1.0 / g_d2h, 1.0 / g_both], device=dev)
+        link = {"h2d_gbs_per_gpu_all_ranks_busy": 1.0 / inv[0], "d2h_gbs_per_gpu_all_ranks_busy": 1.0 / inv[1],
+                "bidirectional_gbs_each_way_per_gpu_all_ranks_busy": 1.0 / inv[2],
+                "how": "256 MiB pinned cudaMemcpyAsync, 4 repetitions, every rank at once, slowest rank reported"}
+        del hsrc, hdst, dbuf, dbuf2
+    except Exception as e:  # noqa: BLE001
+        link = {"unavailable": repr(e)[:120]}
     peak, peak_src = peaks()
     extras = None
     if not args.no_extras:
@@ -504,6 +552,7 @@ def run_ours(args):
                 "pcie_h2d_gbs_per_gpu": e2e_fps / world * h2d_per_frame / 1e9,
                 "pcie_d2h_gbs_per_gpu": e2e_fps / world * out_bytes / 1e9,
                 "staged_pcie_h2d_gbs_per_gpu": e2e_staged_fps / world * (W * H * 3 // 2) / 1e9,
+                "link": link,
                 "note": "zero_copy: the fused kernel reads the pinned host frames in place, so only the source rows its "
                         "taps touch cross PCIe (h2d bytes = plan fetch_bytes_per_frame), and stores the outputs straight "
                         "into the pinned host buffers; staged_h2d: whole-frame cudaMemcpy H2D + cudaMemcpy D2H of every "

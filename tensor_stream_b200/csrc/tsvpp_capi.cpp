@@ -1249,8 +1249,14 @@ static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n
     int rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
     if (rc == TSVPP_OK) {
         (void)cudaGetLastError();
+        // the vectorised kernels need regular geometry and alignment; everything else takes the generic ones
+        bool fast = !env_int("TSVPP_YUV_GENERIC", 0) && w % 8 == 0 && w >= 16 && hgt % 2 == 0 && hgt >= 2 && pitch % 8 == 0 &&
+                    y_bytes >= (long)pitch * (hgt - 1) + w && uv_bytes >= (long)pitch * (hgt / 2 - 1) + w &&
+                    (size_t)(4 + 2) * (size_t)w <= 48 * 1024;
+        for (int i = 0; i < n && fast; ++i)
+            if (((uintptr_t)h[i].y & 7) || ((uintptr_t)h[i].uv & 7) || ((uintptr_t)h[i].out & 15)) fast = false;
         rc = launch_packed_yuv(p->fourcc == TSVPP_YUV444, is_float, ctx->ring_dev[slot], n, w, hgt, pitch, y_bytes,
-                               uv_bytes, is_float, stream);
+                               uv_bytes, is_float, fast ? 1 : 0, stream);
         release_slot(ctx, slot, stream);
         ctx->launches.fetch_add(1);
         if (rc) note_error(rc, "launch_packed_yuv", __LINE__);

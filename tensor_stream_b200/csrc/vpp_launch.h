@@ -17,7 +17,7 @@ int launch_fused(int rs, int ok, bool bulk, const PlanDev &P, const FrameDev *fr
                  int grid, size_t smem_bytes, cudaStream_t stream);
 int launch_direct(int ok, const PlanDev &P, const FrameDev *frames_dev, int nframes, int vec_ok, cudaStream_t stream);
 int launch_packed_yuv(int yuv444, int is_float, const FrameDev *frames_dev, int nframes, int w, int h, int pitch,
-                      long y_bytes, long uv_bytes, int norm, cudaStream_t stream);
+                      long y_bytes, long uv_bytes, int norm, int fast, cudaStream_t stream);
 void launch_pow23(const double *w_dev, double *w2_dev, double *w3_dev, int n, cudaStream_t stream);
 void launch_bicubic_weights(const double *w_dev, double *c_dev, int n, cudaStream_t stream);
 

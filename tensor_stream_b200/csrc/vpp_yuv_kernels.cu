@@ -154,12 +154,182 @@ __global__ void nv12_to_yuv444_kernel(const FrameDev *__restrict__ frames, YuvGe
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fast paths: width % 8 == 0, even height, 8-byte aligned planes / pitch, 16-byte aligned outputs.
+// A thread owns 8 consecutive pixels of one row (4 linear pairs: with an even width pairs never straddle rows).
+// Same arithmetic as the generic kernels above, on packed bytes.
+// ---------------------------------------------------------------------------------------
+// eight chroma bytes U0 V0 U1 V1 | U2 V2 U3 V3 of luma row i at byte column j, vertically filtered on odd chroma
+// rows: (9 (p1 + p2) - (p3 + p4) + 8) >> 4 clamped -- reference src/ColorConversion.cu:107-127 -- evaluated on two
+// 16-bit lanes per register with a bias of 512 per lane (the sum lies in [-502, 4598]): ((s + 512) >> 4) - 32.
+__device__ __forceinline__ uint2 chroma8(const uint8_t *__restrict__ uv, int pitch, int h, int i, int j) {
+    const int r = i >> 1;
+    const uint2 p1 = __ldg(reinterpret_cast<const uint2 *>(uv + (size_t)r * pitch + j));
+    if (!(r & 1)) return p1;
+    const int last = (h >> 1) - 1;
+    const uint2 p2 = __ldg(reinterpret_cast<const uint2 *>(uv + (size_t)min(r + 1, last) * pitch + j));
+    const uint2 p3 = __ldg(reinterpret_cast<const uint2 *>(uv + (size_t)max(r - 1, 0) * pitch + j));
+    const uint2 p4 = __ldg(reinterpret_cast<const uint2 *>(uv + (size_t)min(r + 2, last) * pitch + j));
+    auto filt = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d) -> uint32_t {
+        uint32_t out = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // even bytes, then odd bytes, as two 16-bit lanes
+            const int sh = 8 * half;
+            const uint32_t ae = (a >> sh) & 0x00ff00ffu, be = (b >> sh) & 0x00ff00ffu;
+            const uint32_t ce = (c >> sh) & 0x00ff00ffu, de = (d >> sh) & 0x00ff00ffu;
+            const uint32_t s = 9u * (ae + be) + 0x02080208u - (ce + de);  // + 8 + 512 per lane: no borrow between lanes
+            uint32_t w = (s >> 4) & 0x0fff0fffu;                          // floor(s / 16) + 32 per lane
+            w = __vsub2(__vmaxu2(w, 0x00200020u), 0x00200020u);           // max(x, 0)
+            w = __vminu2(w, 0x00ff00ffu);
+            out |= w << sh;
+        }
+        return out;
+    };
+    return make_uint2(filt(p1.x, p2.x, p3.x, p4.x), filt(p1.y, p2.y, p3.y, p4.y));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nv12_to_uyvy_fast_kernel(const FrameDev *__restrict__ frames, YuvGeom g) {
+    const FrameDev fr = frames[blockIdx.y];
+    const int gpr = g.w >> 3;  // 8-pixel groups per row
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)(gpr * g.h)) return;
+    const int i = (int)(t / (unsigned)gpr), j = 8 * (int)(t - (unsigned)i * (unsigned)gpr);
+    const uint2 y = __ldg(reinterpret_cast<const uint2 *>(fr.y + (size_t)i * g.pitch + j));
+    const uint2 c = chroma8(fr.uv, g.pitch, g.h, i, j);
+    const size_t o = 2 * ((size_t)i * g.w + j);
+    if (sizeof(T) == 1) {
+        // U0 Y0 V0 Y1 | U1 Y2 V1 Y3 | U2 Y4 V2 Y5 | U3 Y6 V3 Y7
+        const uint4 w = make_uint4(__byte_perm(c.x, y.x, 0x5140), __byte_perm(c.x, y.x, 0x7362),
+                                   __byte_perm(c.y, y.y, 0x5140), __byte_perm(c.y, y.y, 0x7362));
+        __stcs(reinterpret_cast<uint4 *>((uint8_t *)fr.out + o), w);
+    } else {
+        float *of = (float *)fr.out + o;
+        const uint32_t cw[2] = {c.x, c.y}, yw[2] = {y.x, y.y};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // pair q: U, Y, V, Y
+            const int u = (int)((cw[q >> 1] >> (16 * (q & 1))) & 0xffu), v = (int)((cw[q >> 1] >> (16 * (q & 1) + 8)) & 0xffu);
+            const int y0 = (int)((yw[q >> 1] >> (16 * (q & 1))) & 0xffu), y1 = (int)((yw[q >> 1] >> (16 * (q & 1) + 8)) & 0xffu);
+            float4 f = make_float4((float)u, (float)y0, (float)v, (float)y1);
+            if (g.norm) f = make_float4(div255f(u), div255f(y0), div255f(v), div255f(y1));
+            __stcs(reinterpret_cast<float4 *>(of) + q, f);
+        }
+    }
+}
+
+// 4:4:4 planar.  The odd pixels' chroma is filtered over the pairs k-1, k, k+1, k+2 in LINEAR order (the
+// reference filters its UYVY temp as one long array: src/ColorConversion.cu:129-143), so a block first builds the
+// vertically filtered pair stream of its rows -- plus the last pair of the row before and the first two of the row
+// after -- in shared memory, then filters from there.  kRows rows per block.
+constexpr int kYuv444Rows = 4;
+template <typename T>
+__global__ void __launch_bounds__(256) nv12_to_yuv444_fast_kernel(const FrameDev *__restrict__ frames, YuvGeom g) {
+    extern __shared__ __align__(16) unsigned char sm444[];  // [(kRows + 2) * w] chroma bytes, row-major, halo rows first/last
+    const FrameDev fr = frames[blockIdx.y];
+    const int w = g.w, h = g.h, gpr = w >> 3;
+    const int i0 = blockIdx.x * kYuv444Rows;
+    const int nrows = min(kYuv444Rows, h - i0);
+    // phase 1: rows i0-1 .. i0+nrows (halo rows only where they exist; what the filter reads outside the image is 0)
+    for (int t = threadIdx.x; t < (nrows + 2) * gpr; t += blockDim.x) {
+        const int lr = t / gpr, j = 8 * (t - lr * gpr);
+        const int i = i0 - 1 + lr;
+        uint2 c = make_uint2(0u, 0u);
+        const bool halo = lr == 0 || lr == nrows + 1;
+        if (i >= 0 && i < h && (!halo || (lr == 0 ? j == w - 8 : j == 0))) c = chroma8(fr.uv, g.pitch, h, i, j);
+        *reinterpret_cast<uint2 *>(sm444 + (size_t)lr * w + j) = c;
+    }
+    __syncthreads();
+    const long npx = (long)w * h;
+    for (int t = threadIdx.x; t < nrows * gpr; t += blockDim.x) {
+        const int lr = t / gpr, j = 8 * (t - lr * gpr);
+        const int i = i0 + lr;
+        const uint2 y = __ldg(reinterpret_cast<const uint2 *>(fr.y + (size_t)i * g.pitch + j));
+        const unsigned char *row = sm444 + (size_t)(lr + 1) * w;  // pair p of this row: bytes row[2p], row[2p+1]
+        const long idx0 = (long)i * w + j;
+        int U[8], V[8];
+        float Uf[8], Vf[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jp = j + 2 * q;  // byte column of pair k = (idx0 + 2q) / 2 inside this row
+            // even pixel 2q: the pair's own (vertically filtered) chroma
+            U[2 * q] = row[jp];
+            V[2 * q] = row[jp + 1];
+            Uf[2 * q] = (float)U[2 * q];
+            Vf[2 * q] = (float)V[2 * q];
+            // odd pixel 2q+1: pairs k-1, k, k+1, k+2; row[-2] / row[w] reach into the halo rows, which hold the
+            // previous row's last pair / the next row's first pairs (or 0 outside the image)
+            const long idx = idx0 + 2 * q + 1;
+            const long si = 2 * idx + 1;
+#pragma unroll
+            for (int comp = 0; comp < 2; ++comp) {
+                const int shift = 2 * comp;
+                const int o3 = (si - 7 + shift < 0) ? 0 : -2;                // point3 < 0 -> point1
+                const int o4 = (si + 5 + shift > 2 * npx - 1) ? 2 : 4;       // point4 past the payload -> point2
+                const int a = row[jp + comp], b = row[jp + 2 + comp], c = row[jp + o3 + comp], d = row[jp + o4 + comp];
+                const int tt = 9 * (a + b) - (c + d) + 8;
+                if (comp == 0) {
+                    U[2 * q + 1] = (tt / 16) & 0xFF;  // C division, narrowed to unsigned char before the clamp: wraps
+                    Uf[2 * q + 1] = fminf(fmaxf((float)tt / 16.0f, 0.0f), 255.0f);
+                } else {
+                    V[2 * q + 1] = (tt / 16) & 0xFF;
+                    Vf[2 * q + 1] = fminf(fmaxf((float)tt / 16.0f, 0.0f), 255.0f);
+                }
+            }
+        }
+        if (sizeof(T) == 1) {
+            uint8_t *o = (uint8_t *)fr.out;
+            auto pk = [](const int (&e)[8], int k) { return (uint32_t)e[k] | ((uint32_t)e[k + 1] << 8) | ((uint32_t)e[k + 2] << 16) | ((uint32_t)e[k + 3] << 24); };
+            __stcs(reinterpret_cast<uint2 *>(o + idx0), y);
+            __stcs(reinterpret_cast<uint2 *>(o + npx + idx0), make_uint2(pk(U, 0), pk(U, 4)));
+            __stcs(reinterpret_cast<uint2 *>(o + 2 * npx + idx0), make_uint2(pk(V, 0), pk(V, 4)));
+        } else {
+            float *o = (float *)fr.out;
+            float fy[8], fu[8], fv[8];
+            const uint32_t yw[2] = {y.x, y.y};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int yv = (int)((yw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                fy[k] = g.norm ? div255f(yv) : (float)yv;
+                if (k & 1) {  // filtered: keeps the fraction, IEEE division like the reference's `/= 255`
+                    fu[k] = g.norm ? __fdiv_rn(Uf[k], 255.0f) : Uf[k];
+                    fv[k] = g.norm ? __fdiv_rn(Vf[k], 255.0f) : Vf[k];
+                } else {
+                    fu[k] = g.norm ? div255f(U[k]) : Uf[k];
+                    fv[k] = g.norm ? div255f(V[k]) : Vf[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k += 4) {
+                __stcs(reinterpret_cast<float4 *>(o + idx0 + k), make_float4(fy[k], fy[k + 1], fy[k + 2], fy[k + 3]));
+                __stcs(reinterpret_cast<float4 *>(o + npx + idx0 + k), make_float4(fu[k], fu[k + 1], fu[k + 2], fu[k + 3]));
+                __stcs(reinterpret_cast<float4 *>(o + 2 * npx + idx0 + k), make_float4(fv[k], fv[k + 1], fv[k + 2], fv[k + 3]));
+            }
+        }
+    }
+}
+
+// fast != 0: the caller has checked width % 8 == 0, even height, 8-byte aligned planes and pitch, 16-byte aligned
+// outputs, (kYuv444Rows + 2) * w bytes of shared memory available, and planes that cover pitch * rows
 int launch_packed_yuv(int yuv444, int is_float, const FrameDev *frames_dev, int nframes, int w, int h, int pitch,
-                      long y_bytes, long uv_bytes, int norm, cudaStream_t stream) {
+                      long y_bytes, long uv_bytes, int norm, int fast, cudaStream_t stream) {
     YuvGeom g;
     g.w = w; g.h = h; g.pitch = pitch; g.y_bytes = y_bytes; g.uv_bytes = uv_bytes; g.norm = norm;
     const long npx = (long)w * h;
     const int threads = 256;
+    if (fast) {
+        if (yuv444) {
+            const dim3 grid((unsigned)((h + kYuv444Rows - 1) / kYuv444Rows), (unsigned)nframes);
+            const size_t smem = (size_t)(kYuv444Rows + 2) * w;
+            if (is_float) nv12_to_yuv444_fast_kernel<float><<<grid, threads, smem, stream>>>(frames_dev, g);
+            else nv12_to_yuv444_fast_kernel<unsigned char><<<grid, threads, smem, stream>>>(frames_dev, g);
+        } else {
+            const dim3 grid((unsigned)(((long)(w / 8) * h + threads - 1) / threads), (unsigned)nframes);
+            if (is_float) nv12_to_uyvy_fast_kernel<float><<<grid, threads, 0, stream>>>(frames_dev, g);
+            else nv12_to_uyvy_fast_kernel<unsigned char><<<grid, threads, 0, stream>>>(frames_dev, g);
+        }
+        return (int)cudaGetLastError();
+    }
     if (yuv444) {
         dim3 grid((unsigned)((npx + threads - 1) / threads), (unsigned)nframes);
         if (is_float) nv12_to_yuv444_kernel<float><<<grid, threads, 0, stream>>>(frames_dev, g);

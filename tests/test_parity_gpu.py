@@ -634,3 +634,26 @@ def test_two_contexts_on_two_gpus_in_one_process():
     v1.close()
     assert torch.cuda.current_device() == 0
     v0.close()
+
+
+YUV_FAST = [(1920, 1080, 1920), (1280, 720, 1536), (720, 480, 720), (64, 16, 64), (16, 2, 16), (4096, 34, 4096), (1000, 562, 1000), (328, 250, 336)]
+
+
+@pytest.mark.parametrize("fourcc", [G.UYVY, G.YUV444], ids=["uyvy", "yuv444"])
+@pytest.mark.parametrize("norm", [False, True], ids=["u8", "f32"])
+@pytest.mark.parametrize("w,h,pitch", YUV_FAST, ids=["%dx%d_p%d" % g for g in YUV_FAST])
+def test_packed_yuv_vector_kernels(vp, fourcc, norm, w, h, pitch):
+    """The vectorised UYVY / YUV444 kernels (8 pixels per thread, packed-byte vertical filter, shared-memory pair
+    stream for the 4:4:4 horizontal filter) against the oracle and against the generic one-pixel-per-thread kernels
+    (TSVPP_YUV_GENERIC=1), on regular sizes (fast path) and on sizes that must fall back (1000 % 8 != 0)."""
+    kw = dict(fourcc=fourcc, normalization=norm)
+    y, uv = _synthetic(w, h, seed=zlib.crc32(("yuv%d%d%d%d" % (fourcc, w, h, norm)).encode()))
+    want = _mask_undefined(_run_oracle(y, uv, kw), kw, w, h)
+    got = _mask_undefined(_run_cuda(vp, y, uv, kw, pitch), kw, w, h)
+    assert _same(got, want), _diff_report(got, want)
+    os.environ["TSVPP_YUV_GENERIC"] = "1"
+    try:
+        gen = _mask_undefined(_run_cuda(vp, y, uv, kw, pitch), kw, w, h)
+    finally:
+        os.environ.pop("TSVPP_YUV_GENERIC", None)
+    assert _same(got, gen), _diff_report(got, gen)

@@ -49,7 +49,10 @@ def main():
     for name, fp in cfgs:
         shape, es = vpp.output_shape(W, H, fp)
         outs = [torch.empty(shape, dtype=torch.float32 if es == 4 else torch.uint8, device=dev) for _ in range(n)]
-        print(name, "|", v.describe_plan(ys[0], uvs[0], fp))
+        try:
+            print(name, "|", v.describe_plan(ys[0], uvs[0], fp))
+        except vpp.VppError:
+            print(name, "| (packed YUV: no fused plan)")
         b = v.make_batch(list(zip(ys, uvs)), fp, outs)
         for _ in range(3):
             b.run()
