@@ -349,6 +349,85 @@ __device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev 
     if (lane == 0) mbar_arrive(bar);  // the "full" barrier counts one arrival per producer warp
 }
 
+// Fill for frames whose base / pitch are NOT 16-byte aligned (tight odd-width clips, sliced tensors): still the TMA
+// unit.  A bulk copy needs 16-byte aligned source, destination and size, so every row segment is fetched as its
+// 16-byte aligned SUPERSET [src & ~15, round_up(src + len, 16)) into the slot, and the consumers are told where the
+// segment starts inside the slot (`shifts`, one byte per slot, written before the barrier arrive).  Only rows whose
+// superset would leave the plane (the first bytes of the first row, the last bytes of the last one) are copied by the
+// warp with guarded loads.  Slots are dealt round-robin to the producer warps; the "full" barrier counts one arrival
+// per producer warp plus the bulk bytes.
+struct ShiftedRow {  // where a slot's row segment lives and how its aligned superset is fetched
+    const unsigned char *plane;
+    long base, pbytes, s0;
+    int len, mis, nbytes;
+    bool bulk;
+};
+template <bool NEED_UV>
+__device__ __forceinline__ ShiftedRow shifted_row(const PlanDev &P, const FrameDev &fr, const int *rs_l, const int *rs_c,
+                                                  int nl, int a0l, int lenl, int a0c, int lenc, int c) {
+    ShiftedRow r;
+    const bool luma = !NEED_UV || c < nl;
+    r.plane = luma ? fr.y : fr.uv;
+    r.base = luma ? (long)rs_l[c] * P.pitch_y + a0l : (long)rs_c[c - nl] * P.pitch_uv + a0c;
+    r.len = luma ? lenl : lenc;
+    r.pbytes = luma ? P.plane_bytes_y : P.plane_bytes_uv;
+    r.mis = (int)((reinterpret_cast<uintptr_t>(r.plane) + (uintptr_t)r.base) & 15);
+    r.s0 = r.base - r.mis;
+    r.nbytes = (r.mis + r.len + 15) & ~15;
+    r.bulk = r.s0 >= 0 && r.s0 + r.nbytes <= r.pbytes;
+    return r;
+}
+template <bool NEED_UV>
+__device__ __forceinline__ void fill_stage_shifted(const PlanDev &P, const FrameDev *__restrict__ frames,
+                                                   const ItemIter &ic, unsigned char *stage, unsigned char *shifts,
+                                                   uint64_t *bar, int lane, uint64_t policy, int pwarp, int npwarps) {
+    const FrameDev fr = frames[ic.frame];
+    const int nl = 2 * P.rp * P.K;
+    const int nc = NEED_UV ? P.rp * P.K : 0;
+    const int a0l = P.seg_a0_l[ic.tile], lenl = P.seg_len_l[ic.tile];
+    const int a0c = NEED_UV ? P.seg_a0_c[ic.tile] : 0, lenc = NEED_UV ? P.seg_len_c[ic.tile] : 0;
+    const int *rs_l = P.rowsrc_l + (size_t)ic.strip * nl;
+    const int *rs_c = P.rowsrc_c + (size_t)ic.strip * nc;
+    const int nslots = nl + nc;
+    // every lane takes one slot of this warp's share (slot = pwarp + npwarps * (32 * round + lane)); rows whose
+    // superset would leave the plane are copied by the whole warp with guarded loads, the others are announced to the
+    // barrier and fetched by one bulk copy per lane
+    uint32_t bytes = 0;
+    for (int c0 = pwarp; c0 < nslots; c0 += 32 * npwarps) {
+        const int c = c0 + npwarps * lane;
+        ShiftedRow r;
+        r.bulk = false;
+        if (c < nslots) {
+            r = shifted_row<NEED_UV>(P, fr, rs_l, rs_c, nl, a0l, lenl, a0c, lenc, c);
+            shifts[c] = r.bulk ? (unsigned char)r.mis : (unsigned char)0;
+            if (r.bulk) bytes += (uint32_t)r.nbytes;
+        }
+        unsigned guarded = __ballot_sync(0xffffffffu, c < nslots && !r.bulk);
+        while (guarded) {
+            const int l = __ffs(guarded) - 1;
+            guarded &= guarded - 1;
+            const int cg = c0 + npwarps * l;
+            const ShiftedRow g = shifted_row<NEED_UV>(P, fr, rs_l, rs_c, nl, a0l, lenl, a0c, lenc, cg);
+            copy_row_ldg(stage + (size_t)cg * P.slot_stride, g.plane, g.base, g.len, g.pbytes, lane);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+    __syncwarp();
+    if (lane == 0) {  // shift bytes and guarded rows are released to the consumers with this arrive
+        if (bytes) mbar_expect_tx(bar, bytes);
+        else mbar_arrive(bar);
+    }
+    __syncwarp();
+    for (int c0 = pwarp; c0 < nslots; c0 += 32 * npwarps) {
+        const int c = c0 + npwarps * lane;
+        if (c < nslots) {
+            const ShiftedRow r = shifted_row<NEED_UV>(P, fr, rs_l, rs_c, nl, a0l, lenl, a0c, lenc, c);
+            if (r.bulk) bulk_g2s(stage + (size_t)c * P.slot_stride, r.plane + r.s0, (uint32_t)r.nbytes, bar, policy);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Resampling of one output sample (one byte of the reference's resized NV12 image)
 // ---------------------------------------------------------------------------------------
@@ -376,6 +455,24 @@ __device__ __forceinline__ uint32_t smem_base_laundered() {
     return b;
 }
 
+// The slots of one output row: slot k (vertical tap k) starts at base + k * stride, plus -- for stages filled by
+// fill_stage_shifted -- the byte the producer recorded for it.
+template <bool SH>
+struct RowSlots {
+    SPtr base;
+    uint32_t stride;
+    uint32_t sh;  // shared address of the row's first shift byte (SH only)
+    __device__ __forceinline__ SPtr row(int k) const {
+        uint32_t a = base.addr + (uint32_t)k * stride;
+        if constexpr (SH) {
+            uint32_t v;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sh + (uint32_t)k));
+            a += v;
+        }
+        return SPtr{a};
+    }
+};
+
 template <int RS>
 struct ColOf;
 template <>
@@ -390,15 +487,15 @@ struct ColOf<RS_AREA> { using T = ColArea; };
 // AREA window sum with the horizontal extent known at compile time: the KXT horizontal weights stay
 // in registers, the taps are immediate-offset shared loads.  Summation order and rounding are the
 // reference's (rows outer, columns inner; w = px*py; sum = fma(d, w, sum)).
-template <int KXT, int STRIDE>
-__device__ __noinline__ int area_sample(SPtr s0, int slot_stride, int K, const float *__restrict__ px,
+template <int KXT, int STRIDE, bool SH>
+__device__ __noinline__ int area_sample(const RowSlots<SH> sl, int o, int K, const float *__restrict__ px,
                                         const float *__restrict__ py, float div) {
     float pxr[KXT];
 #pragma unroll
     for (int b = 0; b < KXT; ++b) pxr[b] = __ldg(px + b);
     float sum = 0.0f;
     for (int a = 0; a < K; ++a) {
-        const SPtr s = s0 + a * slot_stride;
+        const SPtr s = sl.row(a) + o;
         const float wyv = __ldg(py + a);
 #pragma unroll
         for (int b = 0; b < KXT; ++b) sum = __fmaf_rn(u2f(s[b * STRIDE]), __fmul_rn(pxr[b], wyv), sum);
@@ -410,13 +507,13 @@ __device__ __noinline__ int area_sample(SPtr s0, int slot_stride, int K, const f
 // the vertical weights (luma: i, chroma: ci -- the reference evaluates the *luma-grid* formula
 // at the chroma index, src/Resize.cu:303-310), `stride` is 1 for luma and 2 for chroma bytes,
 // `wy` is the preloaded bilinear vertical weight.
-template <int RS>
-__device__ __forceinline__ int resample(const PlanDev &P, SPtr slots,
+template <int RS, bool SH>
+__device__ __forceinline__ int resample(const PlanDev &P, const RowSlots<SH> &slots,
                                         const typename ColOf<RS>::T &col, int orow, int stride, float wy) {
     if constexpr (RS == RS_NEAREST) {
-        return slots[col.o];
+        return slots.row(0)[col.o];
     } else if constexpr (RS == RS_BILINEAR) {
-        const SPtr s0 = slots, s1 = slots + P.slot_stride;
+        const SPtr s0 = slots.row(0), s1 = slots.row(1);
         return bilinear_px(s0[col.o0], s0[col.o1], s1[col.o0], s1[col.o1], col.w, wy);
     } else if constexpr (RS == RS_BICUBIC) {
         const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
@@ -425,7 +522,7 @@ __device__ __forceinline__ int resample(const PlanDev &P, SPtr slots,
         uint32_t b[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const SPtr s = slots + k * P.slot_stride;
+            const SPtr s = slots.row(k);
             b[k] = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
         }
         const float4 cyf4 = __ldg(reinterpret_cast<const float4 *>(P.cyf) + orow);
@@ -438,33 +535,32 @@ __device__ __forceinline__ int resample(const PlanDev &P, SPtr slots,
         const int prow_y = orow % P.PY;
         const float *py = P.py + (size_t)prow_y * P.K;
         const float div = __ldg(P.area_div + (size_t)prow_y * P.PX + col.prow);
-        const SPtr s0 = slots + col.o;
         if (stride == 1) {
             switch (P.KX) {
-                case 2: return area_sample<2, 1>(s0, P.slot_stride, P.K, px, py, div);
-                case 3: return area_sample<3, 1>(s0, P.slot_stride, P.K, px, py, div);
-                case 4: return area_sample<4, 1>(s0, P.slot_stride, P.K, px, py, div);
-                case 5: return area_sample<5, 1>(s0, P.slot_stride, P.K, px, py, div);
-                case 6: return area_sample<6, 1>(s0, P.slot_stride, P.K, px, py, div);
-                case 7: return area_sample<7, 1>(s0, P.slot_stride, P.K, px, py, div);
-                case 8: return area_sample<8, 1>(s0, P.slot_stride, P.K, px, py, div);
+                case 2: return area_sample<2, 1, SH>(slots, col.o, P.K, px, py, div);
+                case 3: return area_sample<3, 1, SH>(slots, col.o, P.K, px, py, div);
+                case 4: return area_sample<4, 1, SH>(slots, col.o, P.K, px, py, div);
+                case 5: return area_sample<5, 1, SH>(slots, col.o, P.K, px, py, div);
+                case 6: return area_sample<6, 1, SH>(slots, col.o, P.K, px, py, div);
+                case 7: return area_sample<7, 1, SH>(slots, col.o, P.K, px, py, div);
+                case 8: return area_sample<8, 1, SH>(slots, col.o, P.K, px, py, div);
                 default: break;
             }
         } else {
             switch (P.KX) {
-                case 2: return area_sample<2, 2>(s0, P.slot_stride, P.K, px, py, div);
-                case 3: return area_sample<3, 2>(s0, P.slot_stride, P.K, px, py, div);
-                case 4: return area_sample<4, 2>(s0, P.slot_stride, P.K, px, py, div);
-                case 5: return area_sample<5, 2>(s0, P.slot_stride, P.K, px, py, div);
-                case 6: return area_sample<6, 2>(s0, P.slot_stride, P.K, px, py, div);
-                case 7: return area_sample<7, 2>(s0, P.slot_stride, P.K, px, py, div);
-                case 8: return area_sample<8, 2>(s0, P.slot_stride, P.K, px, py, div);
+                case 2: return area_sample<2, 2, SH>(slots, col.o, P.K, px, py, div);
+                case 3: return area_sample<3, 2, SH>(slots, col.o, P.K, px, py, div);
+                case 4: return area_sample<4, 2, SH>(slots, col.o, P.K, px, py, div);
+                case 5: return area_sample<5, 2, SH>(slots, col.o, P.K, px, py, div);
+                case 6: return area_sample<6, 2, SH>(slots, col.o, P.K, px, py, div);
+                case 7: return area_sample<7, 2, SH>(slots, col.o, P.K, px, py, div);
+                case 8: return area_sample<8, 2, SH>(slots, col.o, P.K, px, py, div);
                 default: break;
             }
         }
         float sum = 0.0f;  // generic window width
         for (int a = 0; a < P.K; ++a) {
-            const SPtr s = s0 + a * P.slot_stride;
+            const SPtr s = slots.row(a) + col.o;
             const float wyv = __ldg(py + a);
             for (int b = 0; b < P.KX; ++b) sum = __fmaf_rn(u2f(s[b * stride]), __fmul_rn(__ldg(px + b), wyv), sum);
         }
@@ -476,7 +572,8 @@ __device__ __forceinline__ int resample(const PlanDev &P, SPtr slots,
 // wherever the two rows tap the same source row (`shift`, warp-uniform, from the plan): the sum
 // depends on (source row, column) only, so this is the reference's arithmetic evaluated once
 // instead of twice.
-__device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, SPtr sl0, SPtr sl1,
+template <bool SH>
+__device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, const RowSlots<SH> &sl0, const RowSlots<SH> &sl1,
                                                   const ColBicubic &col, int i0, int shift, bool two_rows, int &y0,
                                                   int &y1) {
     const int o0 = col.o[0], o1 = col.o[1], o2 = col.o[2], o3 = col.o[3];
@@ -485,7 +582,7 @@ __device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, SPtr sl0, SP
     uint32_t b0[4], b1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const SPtr s = sl0 + k * P.slot_stride;
+        const SPtr s = sl0.row(k);
         b0[k] = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
     }
     {
@@ -505,7 +602,7 @@ __device__ __forceinline__ void bicubic_luma_pair(const PlanDev &P, SPtr sl0, SP
         else if (shift == 2 && k <= 1) { reuse = true; v = b0[k + 2 > 3 ? 3 : k + 2]; }
         else if (shift == 3 && k == 0) { reuse = true; v = b0[3]; }
         if (!reuse) {
-            const SPtr s = sl1 + k * P.slot_stride;
+            const SPtr s = sl1.row(k);
             v = (uint32_t)bicubic_dot_fast(cf, col.c, exact_x, s[o0], s[o1], s[o2], s[o3]);
         }
         b1[k] = v;

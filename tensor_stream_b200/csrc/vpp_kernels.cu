@@ -49,7 +49,11 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
     unsigned char *stages = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * P.stage_bytes);
     uint64_t *empty = full + kMaxStages;
-    const int NPROD = P.nprod;  // producer warps (bulk: 1, or 2 when the row segments are short; guarded loads: 4)
+    const int NPROD = P.nprod;  // producer warps (bulk: 1, or 2 when the row segments are short; unaligned frames: 4)
+    // unaligned frames: one byte per slot = where the row segment starts inside its slot (fill_stage_shifted)
+    constexpr bool SH = !BULK;
+    const int nslots_pad = (((NEED_UV ? 3 : 2) * P.rp * P.K) + 15) & ~15;
+    unsigned char *shift_tab = smem + (size_t)NS * P.stage_bytes + 2 * 8 * kMaxStages;
     const int ncons_warps = ((int)blockDim.x >> 5) - NPROD;
 
     const int total = nframes * P.nstrips * P.ntiles;
@@ -79,7 +83,8 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
             if (BULK)
                 issue_stage_bulk<NEED_UV>(P, frames, ic, stage, full + s, lane, policy, warp, NPROD);
             else
-                fill_stage_ldg<NEED_UV>(P, frames, ic, stage, full + s, lane, warp, NPROD);
+                fill_stage_shifted<NEED_UV>(P, frames, ic, stage, shift_tab + (size_t)s * nslots_pad, full + s, lane, policy,
+                                            warp, NPROD);
             if (++s == NS) {
                 s = 0;
                 phase ^= 1u;
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
         bool sampled = false;
         if constexpr (RS == RS_NEAREST && SMALL_COL) {
             // no horizontal resize: the block's bytes are consecutive and aligned in the staged rows
-            if (work && P.ident && nx == BW && ny == 2 && (!NEED_UV || (ci < P.ch2 && (j0 >> 1) + BW / 2 <= P.cw2))) {
+            if (!SH && work && P.ident && nx == BW && ny == 2 && (!NEED_UV || (ci < P.ch2 && (j0 >> 1) + BW / 2 <= P.cw2))) {
                 const SPtr sl0 = stage + ((2 * ty) * P.slot_stride + lreg[0].o);
                 const uint32_t w0 = ld_group<BW>(sl0), w1 = ld_group<BW>(sl0 + P.slot_stride);
 #pragma unroll
@@ -164,8 +169,9 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
             }
         }
         if (work && !sampled) {
-            const SPtr sl0 = stage + (2 * ty) * P.K * P.slot_stride;
-            const SPtr sl1 = sl0 + P.K * P.slot_stride;
+            const uint32_t shs = sbase + (uint32_t)(NS * P.stage_bytes + 2 * 8 * kMaxStages + s * nslots_pad);  // this stage's shift bytes
+            const RowSlots<SH> sl0{stage + (2 * ty) * P.K * P.slot_stride, (uint32_t)P.slot_stride, shs + (uint32_t)((2 * ty) * P.K)};
+            const RowSlots<SH> sl1{sl0.base + P.K * P.slot_stride, (uint32_t)P.slot_stride, sl0.sh + (uint32_t)P.K};
 #pragma unroll
             for (int b = 0; b < BW; ++b) {
                 if (b < nx) {
@@ -173,20 +179,21 @@ __global__ void __launch_bounds__((BW == 4 ? 160 : kMaxThreads) + (BULK ? (BW ==
                     if constexpr (RS == RS_BICUBIC) {
                         bicubic_luma_pair(P, sl0, sl1, L, i0, row_shift, ny > 1, Yv[0][b], Yv[1][b]);
                     } else {
-                        Yv[0][b] = resample<RS>(P, sl0, L, i0, 1, wy0);
-                        if (ny > 1) Yv[1][b] = resample<RS>(P, sl1, L, i0 + 1, 1, wy1);
+                        Yv[0][b] = resample<RS, SH>(P, sl0, L, i0, 1, wy0);
+                        if (ny > 1) Yv[1][b] = resample<RS, SH>(P, sl1, L, i0 + 1, 1, wy1);
                     }
                 }
             }
             if (NEED_UV && ci < P.ch2) {
-                const SPtr sc = stage + (2 * P.rp + ty) * P.K * P.slot_stride;
+                const RowSlots<SH> sc{stage + (2 * P.rp + ty) * P.K * P.slot_stride, (uint32_t)P.slot_stride,
+                                      shs + (uint32_t)((2 * P.rp + ty) * P.K)};
 #pragma unroll
                 for (int p = 0; p < BW / 2; ++p) {
                     if ((j0 >> 1) + p < P.cw2) {
                         const ColT &C0 = SMALL_COL ? creg[2 * p] : col_c[colbase + 2 * p];
                         const ColT &C1 = SMALL_COL ? creg[2 * p + 1] : col_c[colbase + 2 * p + 1];
-                        UV[p][0] = resample<RS>(P, sc, C0, ci, 2, wyc);
-                        UV[p][1] = resample<RS>(P, sc, C1, ci, 2, wyc);
+                        UV[p][0] = resample<RS, SH>(P, sc, C0, ci, 2, wyc);
+                        UV[p][1] = resample<RS, SH>(P, sc, C1, ci, 2, wyc);
                     }
                 }
             }
@@ -422,7 +429,9 @@ int fused_block_threads(const PlanDev &P) {
 }
 
 size_t fused_smem_bytes(const PlanDev &P) {
-    return (size_t)P.nstages * P.stage_bytes + 2 * 8 * kMaxStages + 128;
+    // stages, 2 x kMaxStages mbarriers, and (always reserved, used for unaligned frames) one shift byte per slot and stage
+    const int nslots_pad = (((P.need_uv ? 3 : 2) * P.rp * P.K) + 15) & ~15;
+    return (size_t)P.nstages * P.stage_bytes + 2 * 8 * kMaxStages + (size_t)P.nstages * nslots_pad + 128;
 }
 
 // the dynamic-shared-memory opt-in is a per-FUNCTION attribute shared by every plan that uses

@@ -137,7 +137,7 @@ def _diff_report(a, b):
 SUPPORTED_CRC = [c for c in G.CRC_CASES if c[1].get("fourcc", G.RGB24) not in UNSUPPORTED_FOURCC]
 
 
-@pytest.mark.parametrize("pitch", [1080, 1088, 1280], ids=["tight_ldg", "pitch1088_bulk", "pitch1280_bulk"])
+@pytest.mark.parametrize("pitch", [1080, 1088, 1280], ids=["tight_shifted", "pitch1088_bulk", "pitch1280_bulk"])
 @pytest.mark.parametrize("name,kw,crcs,cite", SUPPORTED_CRC, ids=[c[0] for c in SUPPORTED_CRC])
 def test_golden_crc_cuda(vp, golden_frame, name, kw, crcs, cite, pitch):
     from oracle import oracle as O
@@ -202,7 +202,7 @@ SYNTH += [
     ("tiny_output", 1280, 720, 1280, dict(dst=(2, 2), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
     ("small_source", 64, 48, 64, dict(dst=(256, 256), resize_type=G.BICUBIC)),
     ("area_1080p_299", 1920, 1080, 1920, dict(dst=(299, 299), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
-    ("unaligned_pitch_ldg", 1000, 600, 1004, dict(dst=(320, 240), resize_type=G.BILINEAR)),
+    ("unaligned_pitch_shifted", 1000, 600, 1004, dict(dst=(320, 240), resize_type=G.BILINEAR)),
     ("uyvy_noresize_pitch", 1280, 720, 1536, dict(fourcc=G.UYVY)),
     ("yuv444_noresize_f32", 640, 360, 640, dict(fourcc=G.YUV444, normalization=True)),
     ("yuv444_crop_bicubic", 1280, 720, 1280, dict(crop=(64, 32, 704, 512), dst=(320, 200), resize_type=G.BICUBIC, fourcc=G.YUV444)),
@@ -657,3 +657,35 @@ def test_packed_yuv_vector_kernels(vp, fourcc, norm, w, h, pitch):
     finally:
         os.environ.pop("TSVPP_YUV_GENERIC", None)
     assert _same(got, gen), _diff_report(got, gen)
+
+
+
+UNALIGNED = [(o, p) for o in (0, 1, 4, 7, 8, 13, 15) for p in (640, 641, 644, 650, 655)]
+
+
+@pytest.mark.parametrize("kw", [dict(dst=(200, 120), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True),
+                                dict(dst=(320, 240), resize_type=G.NEAREST), dict(fourcc=G.RGB24),
+                                dict(dst=(300, 170), resize_type=G.BICUBIC), dict(dst=(91, 77), resize_type=G.AREA),
+                                dict(crop=(3, 5, 603, 355), dst=(150, 100), resize_type=G.BILINEAR, fourcc=G.HSV)],
+                         ids=["bilinear", "nearest", "noresize", "bicubic_float", "area_float", "crop_hsv"])
+def test_unaligned_frames_bulk_shifted_fill(vp, kw):
+    """Frames whose base address and / or pitch are not multiples of 16 (tight odd-width clips, sliced tensors):
+    row segments are bulk-copied as their 16-byte aligned supersets and the consumers apply the per-slot shift
+    (fill_stage_shifted); the first and last rows of a plane, whose superset would leave it, take guarded loads.
+    Every (offset, pitch) residue class against the oracle."""
+    w, h = 640, 360
+    y, uv = _synthetic(w, h, seed=zlib.crc32(repr(sorted(kw.items())).encode()))
+    want = _mask_undefined(_run_oracle(y, uv, kw), kw, w, h)
+    for off, pitch in UNALIGNED:
+        # planes carved out of one buffer so that reads just outside a plane hit neighbouring data, not zeros
+        buf = torch.full((off + pitch * (h + h // 2) + 16,), 0xAB, dtype=torch.uint8, device="cuda")
+        ty = buf[off:off + pitch * h].view(h, pitch)
+        tuv = buf[off + pitch * h:off + pitch * (h + h // 2)].view(h // 2, pitch)
+        ty[:, :w] = torch.from_numpy(y).cuda()
+        tuv[:, :w] = torch.from_numpy(uv).cuda()
+        if pitch % 16 or off % 16:
+            assert "fill=bulk-shifted" in vp.describe_plan(ty, tuv, _params(kw), width=w, height=h)
+        out = vp.convert(ty, tuv, _params(kw), width=w, height=h)
+        torch.cuda.synchronize()
+        got = _mask_undefined(out.cpu().numpy().reshape(-1), kw, w, h)
+        assert _same(got, want), "offset %d pitch %d: %s" % (off, pitch, _diff_report(got, want))
