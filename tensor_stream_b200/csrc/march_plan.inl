@@ -352,7 +352,7 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
     size_t off_row_l = 0, off_row_c = 0, off_gfl = 0, off_gfc = 0;
     int rows[64];
     if (bilinear) {
-        std::vector<MarchRowL> rl((size_t)nstrips * R, MarchRowL{0, 0, 0, 0}), rc((size_t)std::max(1, nstrips * (R / 2)), MarchRowL{0, 0, 0, 0});
+        std::vector<MarchRowL> rl((size_t)nstrips * R + 2, MarchRowL{0}), rc((size_t)std::max(1, nstrips * (R / 2)) + 2, MarchRowL{0});
         std::vector<int> gfl((size_t)nstrips * G, 0), gfc((size_t)nstrips * G, 0);
         // the two-row window {marched - 1, marched}; taps are folded onto it like the bicubic ones (the bottom
         // border pulls a row's taps back: yDiff = 0, src/Resize.cu:9-10)
@@ -364,9 +364,8 @@ static int build_march(const MarchInputs &in, int sm_count, MarchPlanHost &out) 
             w[1 - (marched - s0)] += (1 << ey) - my;
             w[1 - (marched - s1)] += my;
             if (first_out) *first_out = std::min(s0, s1);
-            r.marched = marched;
-            r.w_old = w[0];
-            r.w_new = w[1];
+            if (marched > 0xffff || w[0] > 255 || w[1] > 255) return false;
+            r.packed = (unsigned)marched | ((unsigned)w[0] << 16) | ((unsigned)w[1] << 24);
             return true;
         };
         for (int st = 0; st < nstrips; ++st) {

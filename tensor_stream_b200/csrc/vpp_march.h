@@ -76,10 +76,8 @@ struct MarchColL {  // one luma column, or one chroma pair
     unsigned w;     // byte 0 = weight of tap 0 (2^ex - mx, or 2^ex when the taps coincide), byte 1 = weight of tap 1
 };
 struct MarchRowL {
-    int marched;  // strip-relative slot the two-row window must have been marched to
-    int w_old;    // weight of the older row of the window (0 .. 2^ey)
-    int w_new;    // weight of the newest row
-    int pad;
+    unsigned packed;  // bits 0-15: strip-relative slot the two-row window must have been marched to;
+                      // bits 16-23: weight of the older row of the window (0 .. 2^ey <= 128); bits 24-31: of the newest
 };
 // area: per output row
 struct MarchRowA {

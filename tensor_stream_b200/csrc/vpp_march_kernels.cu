@@ -389,20 +389,30 @@ __device__ __forceinline__ void march_bilinear_group(const MarchPlanDev &P, cons
     int curc = NEED_UV ? __ldg(P.gfirst_c + strip * P.G + g) - 1 : 0;
     uint32_t sl_l = stage + (uint32_t)(curl + 1) * sstride;
     uint32_t sl_c = stage_c + (uint32_t)(curc + 1) * sstride;
+    // row records are one word each; the next pair's three are requested a whole pair ahead (volatile: the loads stay
+    // here instead of being sunk to their first use)
+    auto ldrow = [](const MarchRowL *r) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(r));
+        return v;
+    };
+    uint32_t nra = ldrow(rowl + 2 * pr0), nrb = ldrow(rowl + 2 * pr0 + 1), nrc = NEED_UV ? ldrow(rowc + pr0) : 0u;
     for (int p = 0; p < rpg; ++p) {
         const int pr = pr0 + p;
         const int i0 = 2 * pr;
         if (i0 >= dh) break;
-        const int4 ra = __ldg(reinterpret_cast<const int4 *>(rowl + i0));
-        const int4 rb = __ldg(reinterpret_cast<const int4 *>(rowl + i0 + 1));
-        int4 rc = make_int4(0, 0, 0, 0);
-        if (NEED_UV) rc = __ldg(reinterpret_cast<const int4 *>(rowc + pr));
+        const uint32_t ra = nra, rb = nrb, rc = nrc;
+        if (p + 1 < rpg) {  // tables are padded by two rows
+            nra = ldrow(rowl + i0 + 2);
+            nrb = ldrow(rowl + i0 + 3);
+            if (NEED_UV) nrc = ldrow(rowc + pr + 1);
+        }
         int Yv[2][4];
         int UV[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-            const int4 r = a ? rb : ra;
-            for (int n = r.x - curl; n > 0; --n, ++curl, sl_l += sstride) {  // uniform
+            const uint32_t r = a ? rb : ra;
+            for (int n = (int)(r & 0xffffu) - curl; n > 0; --n, ++curl, sl_l += sstride) {  // uniform
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t t = __byte_perm(lds32(sl_l + lc.addr[c]), lds32(sl_l + lc.addr[c] + 4), lc.sel[c]);
@@ -410,11 +420,12 @@ __device__ __forceinline__ void march_bilinear_group(const MarchPlanDev &P, cons
                     H1[c] = dp4a_uu(t, lc.w[c], 0u);
                 }
             }
+            const uint32_t w0 = (r >> 16) & 0xffu, w1 = r >> 24;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) Yv[a][c] = (int)((H0[c] * (uint32_t)r.y + H1[c] * (uint32_t)r.z) >> vsh);
+            for (int c = 0; c < 4; ++c) Yv[a][c] = (int)((H0[c] * w0 + H1[c] * w1) >> vsh);
         }
         if (NEED_UV && pr < ch2) {
-            for (int n = rc.x - curc; n > 0; --n, ++curc, sl_c += sstride) {
+            for (int n = (int)(rc & 0xffffu) - curc; n > 0; --n, ++curc, sl_c += sstride) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const uint32_t x0 = lds32(sl_c + lc.caddr[c]), x1 = lds32(sl_c + lc.caddr[c] + 4);
@@ -427,8 +438,8 @@ __device__ __forceinline__ void march_bilinear_group(const MarchPlanDev &P, cons
 #pragma unroll
             for (int c = 0; c < 2; ++c)
                 if ((j0 >> 1) + c < P.e.cw2) {
-                    UV[c][0] = (int)((U0[c] * (uint32_t)rc.y + U1[c] * (uint32_t)rc.z) >> vsh);
-                    UV[c][1] = (int)((V0[c] * (uint32_t)rc.y + V1[c] * (uint32_t)rc.z) >> vsh);
+                    UV[c][0] = (int)((U0[c] * ((rc >> 16) & 0xffu) + U1[c] * (rc >> 24)) >> vsh);
+                    UV[c][1] = (int)((V0[c] * ((rc >> 16) & 0xffu) + V1[c] * (rc >> 24)) >> vsh);
                 }
         }
         const int nx = min(4, P.e.dw - j0), ny = min(2, dh - i0);
