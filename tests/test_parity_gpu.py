@@ -689,3 +689,27 @@ def test_unaligned_frames_bulk_shifted_fill(vp, kw):
         torch.cuda.synchronize()
         got = _mask_undefined(out.cpu().numpy().reshape(-1), kw, w, h)
         assert _same(got, want), "offset %d pitch %d: %s" % (off, pitch, _diff_report(got, want))
+
+
+def test_simple_cli_example_dump_matches_oracle(tmp_path):
+    """examples/simple.py -- the reference's python_examples/simple.py flags and read() loop -- run the way the
+    reference's PythonTests drive it (tests/src/PythonTests.cpp: run the CLI, CRC the raw dump): 6 frames of the
+    synthetic source, every dumped frame equal to the oracle's conversion of the same frame."""
+    import subprocess
+    import sys
+    from tensor_stream_b200.stream import SyntheticSource
+    root = os.path.dirname(HERE)
+    out = str(tmp_path / "dump")
+    n = 6
+    subprocess.check_call([sys.executable, os.path.join(root, "examples", "simple.py"), "-i", "synthetic://1280x720", "-n", str(n),
+                           "-w", "320", "-h", "180", "-fc", "BGR24", "--planes", "PLANAR", "--resize_type", "AREA",
+                           "--normalize", "True", "-o", out], cwd=str(tmp_path))
+    raw = np.fromfile(out + ".yuv", dtype=np.float32)
+    assert raw.size == n * 3 * 180 * 320
+    src = SyntheticSource(1280, 720, torch.device("cuda", 0))
+    kw = dict(dst=(320, 180), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)
+    for k in range(n):
+        y, uv = src.next_frame()
+        want = _run_oracle(y.cpu().numpy(), uv.cpu().numpy(), kw)
+        got = raw[k * want.size:(k + 1) * want.size]
+        assert _same(got, want), "frame %d: %s" % (k, _diff_report(got, want))
