@@ -77,7 +77,9 @@ def _run_oracle(y, uv, kw):
     """CPU oracle.  For BICUBIC the oracle's pow(w,2)/pow(w,3) are pinned to the values the
     device's libdevice returns (the compiled reference calls that very routine and its 1-ulp
     deviations flip exact .5 ties, see oracle/vpp_oracle.c): record the w arguments, evaluate
-    them on the GPU, install the table, run."""
+    them on the GPU, install the table, run.  The GPU evaluation goes through PyTorch's tensor-tensor pow kernel
+    (the same libdevice routine from a binary this repository did not build), NOT through the product library;
+    test_device_pow_hook_agrees_with_an_independent_libdevice_caller ties the library's own hook to it."""
     from oracle import oracle as O
     if kw.get("resize_type", G.NEAREST) != G.BICUBIC:
         return O.convert(y, uv, **kw)[0]
@@ -87,7 +89,9 @@ def _run_oracle(y, uv, kw):
     O.convert(y, uv, **kw)
     O.pow_record(False)
     w = O.pow_recorded()
-    w2, w3 = vpp.device_pow23(w)
+    tw = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).cuda()
+    w2 = torch.pow(tw, torch.full_like(tw, 2.0)).cpu().numpy()  # tensor exponent: no x*x shortcut
+    w3 = torch.pow(tw, torch.full_like(tw, 3.0)).cpu().numpy()
     O.pow_table_set(w, w2, w3)
     try:
         return O.convert(y, uv, **kw)[0]
@@ -713,3 +717,20 @@ def test_simple_cli_example_dump_matches_oracle(tmp_path):
         want = _run_oracle(y.cpu().numpy(), uv.cpu().numpy(), kw)
         got = raw[k * want.size:(k + 1) * want.size]
         assert _same(got, want), "frame %d: %s" % (k, _diff_report(got, want))
+
+
+def test_device_pow_hook_agrees_with_an_independent_libdevice_caller():
+    """The bicubic oracle is pinned to the device's pow(w,2), pow(w,3) through the library's own test hook
+    (tsvpp_debug_pow23).  PyTorch's tensor-tensor pow kernel calls the same libdevice routine from a binary this
+    repository did not build: the two must agree bit for bit, so the pinning does not lean on product code."""
+    from tensor_stream_b200 import vpp
+    rng = np.random.default_rng(11)
+    w = np.concatenate([rng.random(4096), np.arange(0, 64) / 64.0, np.array([0.25, 0.75, 0.5, 0.125, 0.875, 1.0 / 3.0])])
+    w2, w3 = vpp.device_pow23(w)
+    tw = torch.from_numpy(w).cuda()
+    t2 = torch.pow(tw, torch.full_like(tw, 2.0)).cpu().numpy()  # tensor exponent: no x*x shortcut
+    t3 = torch.pow(tw, torch.full_like(tw, 3.0)).cpu().numpy()
+    assert w2.tobytes() == t2.tobytes() and w3.tobytes() == t3.tobytes()
+    # ... and it is NOT the correctly rounded power everywhere (which is why the pinning exists at all)
+    exact2 = (w.astype(np.longdouble) ** 2).astype(np.float64)
+    print("pow(w,2) differs from the correctly rounded square for %d of %d inputs" % (int((w2 != exact2).sum()), w.size))
