@@ -970,9 +970,11 @@ int get_plan(TsvppContext *ctx, const TsvppFrame &f0, const TsvppParams &p, bool
         std::lock_guard<std::mutex> lk(ctx->mu);
         auto it = ctx->plans.find(key);
         if (it != ctx->plans.end()) {
-            // move to the front of the LRU list (the list is short: max_plans entries)
-            ctx->lru.remove(key);
-            ctx->lru.push_front(key);
+            // move to the front of the LRU list unless it is there already (the steady state of a pipeline)
+            if (!(ctx->lru.front() == key)) {
+                ctx->lru.remove(key);
+                ctx->lru.push_front(key);
+            }
             *out = it->second;
             return TSVPP_OK;
         }
