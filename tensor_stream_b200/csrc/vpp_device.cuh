@@ -299,10 +299,8 @@ __device__ __forceinline__ void issue_stage_bulk(const PlanDev &P, const FrameDe
     }
 }
 
-// Fallback fill for frames whose base/pitch are not 16-byte aligned: the producer warp copies each
-// row segment with aligned 32-bit global loads + funnel shifts (any source alignment; bytes outside
-// the plane read as 0), then a plain mbarrier arrive.  Slower than the TMA path by design: NVDEC
-// surfaces and torch tensors with 16-byte-multiple pitches take the bulk path.
+// Guarded row copy: the warp copies one row segment with aligned 32-bit global loads + funnel shifts (any source
+// alignment; bytes outside the plane read as 0).  Used by fill_stage_shifted for the rows at the edges of a plane.
 __device__ __forceinline__ uint32_t ld_word_guarded(const unsigned char *plane, long off, long plane_bytes) {
     // the 4 bytes plane[off .. off+3]; `plane + off` is 4-byte aligned
     if (off >= 0 && off + 4 <= plane_bytes) return __ldg(reinterpret_cast<const uint32_t *>(plane + off));
@@ -325,28 +323,6 @@ __device__ __forceinline__ void copy_row_ldg(unsigned char *dst, const unsigned 
         const uint32_t hi = mis ? ld_word_guarded(plane, abase + 4L * k + 4, plane_bytes) : 0u;
         d32[k] = __funnelshift_r(lo, hi, mis * 8);
     }
-}
-
-template <bool NEED_UV>
-__device__ __forceinline__ void fill_stage_ldg(const PlanDev &P, const FrameDev *__restrict__ frames,
-                                               const ItemIter &ic, unsigned char *stage, uint64_t *bar, int lane,
-                                               int pwarp, int npwarps) {
-    const FrameDev fr = frames[ic.frame];
-    const int nl = 2 * P.rp * P.K;
-    const int nc = NEED_UV ? P.rp * P.K : 0;
-    const int a0l = P.seg_a0_l[ic.tile], lenl = P.seg_len_l[ic.tile];
-    const int *rs_l = P.rowsrc_l + (size_t)ic.strip * nl;
-    for (int c = pwarp; c < nl; c += npwarps)  // rows are dealt round-robin to the producer warps
-        copy_row_ldg(stage + (size_t)c * P.slot_stride, fr.y, (long)rs_l[c] * P.pitch_y + a0l, lenl, P.plane_bytes_y, lane);
-    if (NEED_UV) {
-        const int a0c = P.seg_a0_c[ic.tile], lenc = P.seg_len_c[ic.tile];
-        const int *rs_c = P.rowsrc_c + (size_t)ic.strip * nc;
-        for (int c = pwarp; c < nc; c += npwarps)
-            copy_row_ldg(stage + (size_t)(nl + c) * P.slot_stride, fr.uv, (long)rs_c[c] * P.pitch_uv + a0c, lenc,
-                         P.plane_bytes_uv, lane);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);  // the "full" barrier counts one arrival per producer warp
 }
 
 // Fill for frames whose base / pitch are NOT 16-byte aligned (tight odd-width clips, sliced tensors): still the TMA

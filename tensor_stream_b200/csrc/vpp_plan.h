@@ -34,7 +34,7 @@ enum OutKind : int {
 };
 
 constexpr int kMaxThreads = 288;    // 1 producer warp + up to 256 consumer threads (one 2x2 block each)
-constexpr int kLdgProducerWarps = 4;  // guarded-load fallback: the fill is done by 4 producer warps
+constexpr int kLdgProducerWarps = 4;  // unaligned frames (shifted bulk fill): the slots are shared by 4 producer warps
 constexpr int kMaxStages = 8;       // mbarrier ring depth upper bound
 
 // column parameters, one per output sample column (luma: per output x; chroma: per chroma byte)
@@ -58,7 +58,7 @@ struct PlanDev {
     int tw;                 // tile width in output columns (32..256, multiple of 32)
     int ntiles, nstrips;    // work items per frame = nstrips * ntiles
     int rp;                 // row pairs per strip (1 or 2): a strip is 2*rp luma rows, rp chroma rows
-    int nprod;              // producer warps: 1 (TMA bulk fill) or kLdgProducerWarps (guarded-load fill)
+    int nprod;              // producer warps: 1 (aligned frames) or kLdgProducerWarps (unaligned frames, shifted bulk fill)
     int bw;                 // output columns per consumer thread (2 or 4); a thread owns 2 rows x bw columns
     int K;                  // vertical taps = slots per output row
     int KX;                 // horizontal taps (AREA only)
