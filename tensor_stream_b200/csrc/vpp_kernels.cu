@@ -11,8 +11,10 @@
 //                   source-row segment into a ring of shared-memory stages; completion is
 //                   tracked by "full" mbarriers, reuse by "empty" mbarriers.  Only the source
 //                   rows / bytes the taps touch are ever fetched from HBM.
-//                   Frames whose base / pitch are not 16-byte aligned are filled by four producer
-//                   warps with guarded aligned loads + funnel shifts instead (same consumers).
+//                   Frames whose base / pitch are not 16-byte aligned are staged by the TMA unit too:
+//                   four producer warps bulk-copy the 16-byte aligned SUPERSET of every row segment
+//                   and record per slot where the segment starts; the consumers add that byte
+//                   (RowSlots<SH>).  Guarded loads only for the rows at the edges of a plane.
 //   consumer warps: each thread owns a block of 2 rows x BW columns (BW = 2, or 4 for wide outputs
 //                   of the light resamplers): the luma samples and the (U,V) pairs they share
 //                   are resampled from the staged rows with the
