@@ -98,7 +98,10 @@ __device__ __forceinline__ uint32_t pack_sat2(int a, int b, uint32_t c) {
 // as compiled (vpp_device.cuh: bicubic_dot).  `r` is the integer path's result floor(s_exact + 1/2) = n + 1 with
 // s_exact = n + 1/2: the FP64 sum is within 1e-10 of that, so round-half-away of it is n + 1 if it is >= n + 1/2
 // and n otherwise (n + 1/2 is exact in FP64; for n < 0 both clamp to 0) -- no libdevice round() needed.
-__device__ __forceinline__ int bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps, int r) {
+#ifndef TSVPP_TIE_INLINE
+#define TSVPP_TIE_INLINE __forceinline__
+#endif
+__device__ TSVPP_TIE_INLINE int bicubic_tie_fp64(const double *__restrict__ c, uint32_t taps, int r) {
     const double2 c01 = __ldg(reinterpret_cast<const double2 *>(c));
     const double2 c23 = __ldg(reinterpret_cast<const double2 *>(c) + 1);
     double s = __dmul_rn(c01.y, (double)(int)((taps >> 8) & 0xffu));
