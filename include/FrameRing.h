@@ -6,6 +6,7 @@
 //     decoder->GetFrame(index, consumer, frame);  vpp->Convert(frame, out, params, consumer);
 // (src/Wrappers/WrapperPython.cpp:296-312), whose Convert calls this library coalesces into batched launches.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -29,8 +30,9 @@ public:
         av_frame_ref(&frames[slot], &decoded);
         valid[slot] = true;
         currentFrame++;
+        published.store(currentFrame, std::memory_order_release);
         for (auto &item : consumerStatus) item.second = true;
-        consumerSync.notify_all();
+        if (sleepers) consumerSync.notify_all();  // nobody to wake at high rates: consumers that spin see `published`
     }
 
     // reference src/Decoder.cpp:97-131, statement for statement: blocks until a frame newer than the consumer's
@@ -44,8 +46,18 @@ public:
             // frames were published already: hand out the last one without waiting for the next
             if (currentFrame > 0) consumerStatus[consumerName] = true;
         }
-        if (!isFinished)
+        if (!isFinished && !consumerStatus[consumerName]) {
+            // a consumer that is faster than the source first polls the frame counter for a few microseconds (a
+            // futex sleep and wake-up cost more than a frame period at 1e5+ frames/s), then blocks like the reference
+            const unsigned seen = currentFrame;
+            locker.unlock();
+            for (int spin = 0; spin < 4000 && published.load(std::memory_order_acquire) == seen && !finishedFlag.load(); ++spin) {
+            }
+            locker.lock();
+            ++sleepers;
             while (!consumerStatus[consumerName] && !isFinished) consumerSync.wait(locker);
+            --sleepers;
+        }
         if (isFinished) throw std::runtime_error("Decoding finished");
         consumerStatus[consumerName] = false;
         if (index > 0) index = 0;
@@ -60,6 +72,7 @@ public:
         std::unique_lock<std::mutex> locker(sync);
         for (auto &item : consumerStatus) item.second = true;
         isFinished = true;
+        finishedFlag.store(true);
         consumerSync.notify_all();
         return VREADER_OK;
     }
@@ -78,4 +91,7 @@ private:
     std::mutex sync;
     std::condition_variable consumerSync;
     bool isFinished = false;
+    std::atomic<unsigned> published{0};   // = currentFrame, readable without the lock
+    std::atomic<bool> finishedFlag{false};
+    int sleepers = 0;                     // consumers inside consumerSync.wait (guarded by `sync`)
 };

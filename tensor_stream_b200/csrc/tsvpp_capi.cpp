@@ -1368,13 +1368,30 @@ static inline bool co_reached(const TsvppContext *ctx, unsigned seq);
 static void co_thread_main(TsvppContext *ctx) {
     cudaSetDevice(ctx->device);
     const unsigned depth = (unsigned)std::max(1, env_int("TSVPP_CO_DEPTH", 2));
+    // Blocking callers come back in cohorts: the frames of one launch complete together and are resubmitted within
+    // a microsecond or two of each other.  Draining the moment the first of them arrives splits the callers into
+    // `depth + 1` small cohorts for good (8 consumers: batches of 2.6).  So when fewer frames are pending than recent
+    // launches carried, the launcher lingers a few microseconds for the rest of the cohort.
+    const long linger_ns = 1000L * std::max(0, env_int("TSVPP_CO_LINGER_US", 4));
     unsigned idle = 0;
+    int expected = 1;
     while (!ctx->co_stop.load(std::memory_order_acquire)) {
         if (ctx->co_pending.load(std::memory_order_acquire) > 0) {
             // at most `depth` launches in flight: while the stream is that far behind, let the queue grow
             if (ctx->co_memops && !co_reached(ctx, ctx->co_seq - (depth - 1))) continue;
-            std::lock_guard<std::mutex> lk(ctx->co_launch);
-            co_drain(ctx);
+            if (linger_ns > 0 && ctx->co_pending.load(std::memory_order_acquire) < expected) {
+                const auto t0 = std::chrono::steady_clock::now();
+                while (ctx->co_pending.load(std::memory_order_acquire) < expected &&
+                       (std::chrono::steady_clock::now() - t0).count() < linger_ns) {
+                }
+            }
+            const int before = ctx->co_pending.load(std::memory_order_acquire);
+            {
+                std::lock_guard<std::mutex> lk(ctx->co_launch);
+                co_drain(ctx);
+            }
+            expected = std::max(before, expected * 3 / 4);
+            if (expected < 1) expected = 1;
             idle = 0;
         } else if (++idle > 20000) {  // ~100 us without work: sleep until the next frame is posted
             std::unique_lock<std::mutex> lk(ctx->co_cv_mu);
@@ -1384,6 +1401,7 @@ static void co_thread_main(TsvppContext *ctx) {
             });
             ctx->co_sleeping.store(0, std::memory_order_release);
             idle = 0;
+            expected = 1;
         }
     }
 }

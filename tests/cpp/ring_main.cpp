@@ -121,6 +121,9 @@ int main(int argc, char **argv) {
     // RING_OUT=pool: every consumer recycles 32 result buffers of its own through VideoProcessor::ConvertInto (what the
     // ATen hand-off does with torch's caching allocator) -- no allocation, no free, no CUDA call per frame
     const bool pool_out = std::getenv("RING_OUT") && std::string(std::getenv("RING_OUT")) == "pool";
+    // RING_SOURCE=direct: every consumer walks the surface pool by itself (one decoder per consumer, never paced by
+    // another thread) -- isolates what the Convert side can take from what one shared ring can hand out
+    const bool direct_src = std::getenv("RING_SOURCE") && std::string(std::getenv("RING_SOURCE")) == "direct";
     const int kPoolOut = 32;
     const int W = 1920, H = 1080, pitch = 1920, DW = 256, DH = 256, pool = 64;
     // C2: BGR24 planar 256x256 bilinear, normalised float32
@@ -228,15 +231,20 @@ int main(int argc, char **argv) {
             for (int n = 0; n < per; ++n) {
                 AVFrame in, out;
                 std::memset(&out, 0, sizeof(out));
-                const int sts = ring.GetFrame(index, name, &in);
-                if (sts == VREADER_REPEAT) {
-                    repeats.fetch_add(1);
-                    --n;
-                    continue;
-                }
                 int src = -1;
-                for (int k = 0; k < pool && src < 0; ++k)
-                    if (in.data[0] == ys[k]) src = k;
+                if (direct_src) {
+                    src = (c * 7 + n) % pool;
+                    in = surface(ys[src], uvs[src], W, H, pitch);
+                } else {
+                    const int sts = ring.GetFrame(index, name, &in);
+                    if (sts == VREADER_REPEAT) {
+                        repeats.fetch_add(1);
+                        --n;
+                        continue;
+                    }
+                    for (int k = 0; k < pool && src < 0; ++k)
+                        if (in.data[0] == ys[k]) src = k;
+                }
                 const int rc = pool_out ? vpp.ConvertInto(&in, &out, mine[held.size()], params, name)
                                         : vpp.Convert(&in, &out, params, name);
                 if (rc != VREADER_OK || !out.opaque || out.width != DW || out.height != DH) {
@@ -261,6 +269,7 @@ int main(int argc, char **argv) {
                 total, secs, total / secs, published.load(), repeats.load(), bad.load(),
                 std::getenv("TSVPP_COALESCE") ? std::getenv("TSVPP_COALESCE") : "1",
                 std::getenv("TSVPP_ASYNC") ? std::getenv("TSVPP_ASYNC") : "0", pool_out ? "recycled(ConvertInto)" : free_async ? "cudaFreeAsync" : "cudaFree");
+    if (direct_src) std::printf("source direct (no shared ring)\n");
     vpp.Close();
     return bad.load() ? 1 : 0;
 }
