@@ -294,6 +294,61 @@ def run_extras(torch, vpp, v, dev, pool1080, barrier, max_over_ranks, world, pea
     return out
 
 
+def run_variants(torch, vpp, v, dev, pool1080, fp, barrier, max_over_ranks, world, peak):
+    """SURVEY 8(d) input rules on the headline workload: NVDEC-like pitch (1920 -> 2048), limited-range
+    video-like content, and the frames-per-launch sweep 1 / 8 / 64 (the headline itself is the whole pool)."""
+    out = []
+    stream = torch.cuda.current_stream(dev)
+    ys, uvs = pool1080
+    shape, es = vpp.output_shape(W, H, fp)
+    out_bytes = shape[0] * shape[1] * shape[2] * es
+
+    def timed(name, frames, widths, nf, K):
+        outs = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(nf)]
+        batch = v.make_batch(frames[:nf], fp, outs, widths=widths)
+        for _ in range(3):
+            batch.run(stream)
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        evs[0].record(stream)
+        for k in range(K):
+            batch.run(stream)
+            evs[k + 1].record(stream)
+        barrier()
+        ms = statistics.median(evs[k].elapsed_time(evs[k + 1]) for k in range(K))
+        ms = max_over_ranks([ms], device=dev)[0]
+        batch.destroy()
+        fps1 = nf / (ms * 1e-3)
+        b_full = W * H * 3 // 2 + out_bytes
+        out.append({"workload": name, "fps": fps1 * world, "fps_per_gpu": fps1, "launch_ms_median": ms,
+                    "frames_per_launch": nf, "b_full_bytes_per_frame": b_full,
+                    "gbs_b_full": fps1 * b_full / 1e9, "frac_effective": fps1 * b_full / 1e9 / peak})
+
+    try:
+        nf = min(256, len(ys))
+        g = torch.Generator(device=dev)
+        g.manual_seed(777)
+        py = [torch.randint(0, 256, (H, 2048), dtype=torch.uint8, device=dev, generator=g) for _ in range(nf)]
+        puv = [torch.randint(0, 256, (H // 2, 2048), dtype=torch.uint8, device=dev, generator=g) for _ in range(nf)]
+        timed("C2 variant: NVDEC-like pitch 2048", list(zip(py, puv)), (W, H), nf, 10)
+        del py, puv
+        # limited-range, smooth gradient + noise (the kernels are data-independent; this shows it)
+        ramp = (torch.arange(W, device=dev, dtype=torch.float32)[None, :] * (180.0 / W)
+                + torch.arange(H, device=dev, dtype=torch.float32)[:, None] * (30.0 / H) + 16.0)
+        vy, vuv = [], []
+        for i in range(nf):
+            noise = torch.randint(0, 9, (H, W), device=dev, generator=g).float()
+            vy.append((ramp + noise).clamp(16, 235).to(torch.uint8))
+            vuv.append(torch.randint(112, 145, (H // 2, W), dtype=torch.uint8, device=dev, generator=g))
+        timed("C2 variant: limited-range video-like content", list(zip(vy, vuv)), None, nf, 10)
+        del vy, vuv
+        for k in (1, 8, 64):
+            timed("C2 variant: %d frame%s per launch" % (k, "" if k == 1 else "s"), list(zip(ys, uvs)), None, k, 200)
+    except Exception as e:
+        out.append({"workload": "C2 variants", "error": repr(e)[:200]})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -509,7 +564,9 @@ def run_ours(args):
     extras = None
     if not args.no_extras:
         batch.destroy()
-        extras = run_extras(torch, vpp, v, dev, (ys, uvs), barrier, S.max_over_ranks, world, peak)
+        del outs
+        extras = run_variants(torch, vpp, v, dev, (ys, uvs), fp, barrier, S.max_over_ranks, world, peak)
+        extras += run_extras(torch, vpp, v, dev, (ys, uvs), barrier, S.max_over_ranks, world, peak)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
