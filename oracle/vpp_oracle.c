@@ -431,10 +431,15 @@ static int resize_area_down(const plane_t *Y, const plane_t *UV, int sw, int sh,
     int dw = o->w, dh = o->h;
     float xr = (float)sw / dw, yr = (float)sh / dh;
     int strideX = (int)ceilf(xr), strideY = (int)ceilf(yr);
-    int maxrows = 8192;
-    float *patX = (float *)malloc(sizeof(float) * (size_t)maxrows * strideX);
-    float *patY = (float *)malloc(sizeof(float) * (size_t)maxrows * strideY);
-    int PX = vpo_area_pattern(xr, patX, maxrows), PY = vpo_area_pattern(yr, patY, maxrows);
+    /* the kernel indexes the patterns with j % PX and i % PY (:187-188): a pattern at least as long as the
+     * output never wraps, so generation may stop at dw / dh rows (the reference's loop only ends when
+     * id*scale is integral in f32, which for scales like 2034/508 takes thousands of rows) */
+    float *patX = (float *)malloc(sizeof(float) * (size_t)(dw + 1) * strideX);
+    float *patY = (float *)malloc(sizeof(float) * (size_t)(dh + 1) * strideY);
+    if (!patX || !patY) { free(patX); free(patY); return -1; }
+    int PX = vpo_area_pattern(xr, patX, dw), PY = vpo_area_pattern(yr, patY, dh);
+    if (PX < 0) PX = dw;
+    if (PY < 0) PY = dh;
     if (PX <= 0 || PY <= 0) { free(patX); free(patY); return -1; }
     (void)sh;
     for (int i = 0; i < dh; i++) {
@@ -636,8 +641,13 @@ static void to_nv12_merged(const plane_t *Y, const plane_t *UV, int w, int h, in
     uint8_t *d8 = (uint8_t *)dst;
     float *df = (float *)dst;
     long wh = (long)w * h;
+    /* odd w: the reference's last column writes its V one element past the row -- into the next chroma row
+     * (rewritten by that row's first column; a race on the GPU) and, on the last row, past the
+     * allocation.  Sequential order here; the out-of-bounds store is dropped. */
+    long total = wh + (long)(h / 2) * w;
 #define PUT(idx, v)                                                   \
     do {                                                              \
+        if ((idx) >= total) break;                                    \
         if (as_float) { float f_ = (float)(v); if (norm) f_ /= 255; df[idx] = f_; } \
         else d8[idx] = (uint8_t)(v);                                  \
     } while (0)

@@ -164,14 +164,17 @@ int out_kind_of(const TsvppParams &p) {
 
 // reference src/Resize.cu:359-386 (generateResizePattern); rows are ceil(scale) floats wide,
 // surplus entries dropped as the kernel never reads them (Resize.cu:162-163).
-bool area_pattern(float scale, std::vector<float> &out, int &rows) {
+// The kernel indexes the pattern with (output index % rows): once `need` (= output columns / rows) pattern
+// rows exist the period no longer matters, so generation stops there (some scales, e.g. 2034/508 in f32, only
+// reach an integral id*scale after thousands of rows).
+bool area_pattern(float scale, int need, std::vector<float> &out, int &rows) {
     const int stride = (int)std::ceil(scale);
     const float eps = std::numeric_limits<float>::epsilon();
     int id = 0;
     float rest = 0;
     out.clear();
     while ((float)id * scale == 0 || ((float)id * scale - (float)(int)((float)id * scale) > eps)) {
-        if (id >= (1 << 16)) return false;
+        if (id >= need) break;
         out.resize((size_t)(id + 1) * stride, 0.f);
         float *row = out.data() + (size_t)id * stride;
         float dyn = scale;
@@ -468,7 +471,7 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     int PX = 1, PY = 1;
     int KX = 1, K = 1;
     if (rs == RS_AREA) {
-        if (!area_pattern(xr, patx, PX) || !area_pattern(yr, paty, PY)) return TSVPP_UNSUPPORTED;
+        if (!area_pattern(xr, dw, patx, PX) || !area_pattern(yr, dh, paty, PY)) return TSVPP_UNSUPPORTED;
         KX = (int)std::ceil(xr);
         K = (int)std::ceil(yr);
     } else if (rs == RS_BILINEAR) {
@@ -554,10 +557,13 @@ int build_plan(TsvppContext *ctx, int W, int H, int pitch_y_in, int pitch_uv_in,
     if (bw == 4 && env_int("TSVPP_NPROD", 1) == 2) nprod_bulk = 2;
     const int regs_assumed = bw == 4 ? 80 : ((rs == RS_NEAREST || rs == RS_BILINEAR) ? 56 : 72);  // caps implied by __launch_bounds__
     long best_score = -1;
+    // pass 0: tiles of 32..256 columns.  pass 1, only when no such tile fits (AREA windows of an extreme
+    // downscale: 3 * rp * ceil(yr) row slots of tw * xr bytes): narrower tiles down to one column block.
+    for (int pass = 0; pass < 2 && !found; ++pass)
     for (int cand_rp = 2; cand_rp >= 1; --cand_rp) {
         if (cand_rp == 2 && dh < 4) continue;
         if (env_int("TSVPP_RP", 0) && cand_rp != want_rp) continue;
-        for (int cand = 256; cand >= 32; cand >>= 1) {
+        for (int cand = pass ? 16 : 256; cand >= (pass ? bw : 32); cand >>= 1) {
             if (cand > want_tw) continue;
             if (cand > 32 && cand >= 2 * round_up(dw, 32)) continue;  // don't over-size tiles for narrow outputs
             const int nt = (dw + cand - 1) / cand;

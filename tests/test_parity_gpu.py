@@ -217,6 +217,11 @@ SYNTH += [
     ("src_8k_area_generic_window", 7680, 4320, 7680, dict(dst=(480, 270), resize_type=G.AREA)),
     ("src_8k_bicubic_crop", 7680, 4320, 7680, dict(crop=(1920, 1080, 5760, 3240), dst=(640, 360), resize_type=G.BICUBIC)),
     ("dst_8k_nearest", 1920, 1080, 1920, dict(dst=(7680, 4320), resize_type=G.NEAREST)),
+    # found by tools/fuzz_parity.py: an AREA scale whose f32 pattern period exceeds the output (2034/508: id*scale is
+    # integral only after thousands of rows), and an extreme AREA downscale (44 x 113 tap windows: narrow tiles)
+    ("area_pattern_longer_than_output", 2034, 260, 2034, dict(dst=(508, 64), resize_type=G.AREA, fourcc=G.NV12, planes=G.MERGED)),
+    ("area_extreme_downscale", 1842, 1126, 1965, dict(dst=(42, 10), resize_type=G.AREA, fourcc=G.RGB24, planes=G.PLANAR)),
+    ("area_1080p_to_16x16", 1920, 1080, 1920, dict(dst=(16, 16), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
 ]
 
 

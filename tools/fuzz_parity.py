@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""Randomised parity soak: CUDA path (through the C-ABI) vs the CPU oracle on random geometries, pitches,
+crops, resize types, FourCCs, layouts and normalisation.  Test infrastructure (it imports oracle/ as the
+checker, like tests/); run it on the GPU box:
+
+    python tools/fuzz_parity.py --seconds 300 --seed 1 > gpurun_out/fuzz.log
+
+Every case is reproducible from its printed line (seed + index).  Exit code 1 if any case differs.
+"""
+import argparse
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tests import golden_cases as G  # noqa: E402
+from tests import test_parity_gpu as T  # noqa: E402
+
+
+def even(x):
+    return max(2, int(x) & ~1)
+
+
+def pick_case(rng):
+    r = rng.random()
+    if r < 0.25:
+        w, h = rng.choice([(1920, 1080), (1280, 720), (1080, 608), (640, 360), (960, 540)])
+    elif r < 0.30:
+        w, h = 3840, 2160
+    else:
+        w, h = even(rng.randint(32, 2048)), even(rng.randint(32, 1200))
+    pr = rng.random()
+    if pr < 0.35:
+        pitch = w
+    elif pr < 0.6:
+        a = rng.choice([16, 64, 256, 512])
+        pitch = (w + a - 1) // a * a
+    else:
+        pitch = w + rng.randint(1, 200)
+    kw = {}
+    cw, ch = w, h
+    if rng.random() < 0.4 and w >= 64 and h >= 64:
+        cw, ch = even(rng.randint(16, w - 2)), even(rng.randint(16, h - 2))
+        x0, y0 = even(rng.randint(0, w - cw)) if w - cw >= 2 else 0, even(rng.randint(0, h - ch)) if h - ch >= 2 else 0
+        if x0 + cw > w:
+            x0 = 0
+        if y0 + ch > h:
+            y0 = 0
+        kw["crop"] = (x0, y0, x0 + cw, y0 + ch)
+    dr = rng.random()
+    if dr < 0.15:
+        pass  # no resize
+    else:
+        if dr < 0.45:  # dyadic-friendly targets (integer march kernels)
+            fx, fy = rng.choice([0.25, 0.5, 2.0, 2 / 3, 1.5, 0.125, 4 / 3, 0.75]), rng.choice([0.25, 0.5, 2.0, 2 / 3, 1.5, 0.125, 0.75])
+            dw, dh = even(cw * fx), even(ch * fy)
+        elif dr < 0.6:
+            dw, dh = rng.choice([(256, 256), (128, 128), (224, 224), (299, 299), (512, 512), (720, 480), (1280, 720), (64, 64)])
+        elif dr < 0.9:
+            dw, dh = even(rng.randint(8, 1400)), even(rng.randint(8, 900))
+        else:
+            dw, dh = rng.randint(8, 700), rng.randint(8, 500)  # odd sizes included
+        while dw * dh > 2_500_000:
+            dw, dh = even(dw // 2), even(dh // 2)
+        kw["dst"] = (dw, dh)
+        kw["resize_type"] = rng.choice([G.NEAREST, G.BILINEAR, G.BICUBIC, G.AREA])
+    kw["fourcc"] = rng.choice([G.RGB24, G.BGR24, G.RGB24, G.BGR24, G.Y800, G.HSV, G.NV12, G.UYVY, G.YUV444])
+    kw["planes"] = rng.choice([G.PLANAR, G.MERGED])
+    kw["normalization"] = rng.choice([False, True])
+    if kw["fourcc"] == G.HSV:
+        kw["normalization"] = True
+    dw, dh = kw.get("dst", (cw, ch))
+    if (dw % 2 or dh % 2) and kw["fourcc"] in (G.NV12, G.UYVY, G.YUV444):
+        # odd sizes with the 4:2:0 / 4:2:2 outputs are races / out-of-bounds stores in the reference
+        kw["fourcc"] = G.RGB24
+    return w, h, pitch, kw
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--max-cases", type=int, default=100000)
+    args = ap.parse_args()
+    import torch
+    from tensor_stream_b200 import vpp
+    assert torch.cuda.is_available(), "needs a GPU"
+    v = vpp.VideoProcessor(0)
+    rng = random.Random(args.seed)
+    t0 = time.time()
+    n = ok = bad = rejected = both_rejected = 0
+    kernels = {}
+    for idx in range(args.max_cases):
+        if time.time() - t0 > args.seconds:
+            break
+        w, h, pitch, kw = pick_case(rng)
+        nrng = np.random.default_rng(args.seed * 1000003 + idx)
+        if rng.random() < 0.3:
+            y, uv = T._synthetic(w, h, args.seed * 7919 + idx, video_like=True)
+        else:
+            y = nrng.integers(0, 256, (h, w), dtype=np.uint8)
+            uv = nrng.integers(0, 256, (h // 2, w), dtype=np.uint8)
+        n += 1
+        tag = "case %d seed %d: %dx%d pitch %d %s" % (idx, args.seed, w, h, pitch, kw)
+        try:
+            want = T._run_oracle(y, uv, kw)
+            oracle_err = None
+        except Exception as e:  # noqa: BLE001
+            want, oracle_err = None, e
+        try:
+            got = T._run_cuda(v, y, uv, kw, pitch)
+            cuda_err = None
+        except vpp.VppError as e:
+            got, cuda_err = None, e
+        if cuda_err is not None or oracle_err is not None:
+            if cuda_err is not None and oracle_err is not None:
+                both_rejected += 1
+            else:
+                rejected += 1
+                print("REJECTED by %s only: %s  (%r)" % ("cuda" if cuda_err else "oracle", tag, cuda_err or oracle_err), flush=True)
+            continue
+        try:
+            ty, tuv, _ = T._to_dev(y, uv, pitch)
+            plan = v.describe_plan(ty, tuv, T._params(kw), width=w, height=h)
+            k = " ".join(p for p in plan.split() if p.startswith(("kernel=", "resample=", "bulk=")))
+        except Exception:  # noqa: BLE001
+            k = "no fused plan"
+        kernels[k] = kernels.get(k, 0) + 1
+        a = T._mask_undefined(got, kw, w, h)
+        b = T._mask_undefined(want, kw, w, h)
+        if T._same(a, b):
+            ok += 1
+        else:
+            bad += 1
+            print("MISMATCH %s [%s]: %s" % (tag, k, T._diff_report(np.asarray(a), np.asarray(b))), flush=True)
+    print("cases %d ok %d mismatches %d rejected-by-one-side %d rejected-by-both %d in %.0f s" %
+          (n, ok, bad, rejected, both_rejected, time.time() - t0))
+    for k in sorted(kernels, key=kernels.get, reverse=True):
+        print("  %5d  %s" % (kernels[k], k))
+    v.close()
+    sys.exit(1 if bad or rejected else 0)
+
+
+if __name__ == "__main__":
+    main()
