@@ -1276,6 +1276,86 @@ static int convert_packed_yuv(TsvppContext *ctx, const TsvppFrame *frames, int n
     return rc;
 }
 
+// AREA downscales whose tap window exceeds the fused kernel's shared-memory stages (ratios beyond ~50x: 1080p ->
+// 8x8): the reference's own two stages -- resize into a tight NV12 intermediate (area_wide_kernel), then the
+// colour stage on that intermediate through the ordinary plans.
+static bool area_wide_applies(const TsvppFrame &f0, const TsvppParams &p) {
+    if (validate_geometry(f0.width, f0.height, p)) return false;
+    const Geometry g = resolve_geometry(f0.width, f0.height, p);
+    if (!g.resize || p.resize_type != TSVPP_AREA) return false;
+    const float xr = (float)g.sw / g.dw, yr = (float)g.sh / g.dh;
+    return xr > 1 && yr > 1 && g.dh >= 2;  // the colour stage needs a chroma row under its source (validate_geometry)
+}
+
+static int convert_area_wide(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
+                             void *const *out, cudaStream_t stream, bool frames_on_host) {
+    const int W = frames[0].width, H = frames[0].height;
+    const Geometry g = resolve_geometry(W, H, *p);
+    AreaWideParams A{};
+    A.dw = g.dw; A.dh = g.dh; A.sw = g.sw; A.sh = g.sh;
+    A.crop = g.crop ? 1 : 0; A.x0 = g.x0; A.y0 = g.y0;
+    A.pitch_y = frames[0].pitch_y ? frames[0].pitch_y : W;    // Resize.cu:420-421
+    A.pitch_uv = frames[0].pitch_uv ? frames[0].pitch_uv : W;
+    A.plane_y = (long)A.pitch_y * H;
+    A.plane_uv = (long)A.pitch_uv * (H / 2);
+    A.xr = (float)g.sw / g.dw;
+    A.yr = (float)g.sh / g.dh;
+    A.KX = (int)std::ceil(A.xr);
+    A.K = (int)std::ceil(A.yr);
+    std::vector<float> patx, paty;
+    if (!area_pattern(A.xr, g.dw, patx, A.PX) || !area_pattern(A.yr, g.dh, paty, A.PY)) return TSVPP_UNSUPPORTED;
+    const size_t nx = patx.size(), ny = paty.size();
+    const size_t ybytes = (size_t)g.dw * g.dh;
+    const size_t fbytes = (ybytes + ybytes / 2 + 255) / 256 * 256 + 256;
+    const size_t tab_off = fbytes * (size_t)n;
+    unsigned char *tmp = nullptr;
+    TSVPP_CUDA(cudaMallocAsync(&tmp, tab_off + (nx + ny) * sizeof(float), stream));
+    auto bail = [&](int rc) {
+        cudaFreeAsync(tmp, stream);
+        return rc;
+    };
+    // odd sizes: chroma bytes the resize stage never writes (last column, the row under the last luma row)
+    // must read as 0, like the oracle's intermediate
+    if ((g.dw | g.dh) & 1) {
+        cudaError_t me = cudaMemsetAsync(tmp, 0, tab_off, stream);
+        if (me != cudaSuccess) return bail(note_error((int)me, "cudaMemsetAsync(area intermediate)", __LINE__));
+    }
+    float *tab = reinterpret_cast<float *>(tmp + tab_off);
+    // pageable sources: the runtime stages them before returning, the vectors may go out of scope
+    cudaError_t e = cudaMemcpyAsync(tab, patx.data(), nx * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tab + nx, paty.data(), ny * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return bail(note_error((int)e, "cudaMemcpyAsync(area patterns)", __LINE__));
+    A.patx = tab;
+    A.paty = tab + nx;
+    std::vector<FrameDev> h(n);
+    std::vector<TsvppFrame> f2(n);
+    for (int i = 0; i < n; ++i) {
+        h[i].y = frames[i].y;
+        h[i].uv = frames[i].uv;
+        h[i].out = tmp + fbytes * i;
+        f2[i].y = tmp + fbytes * i;
+        f2[i].uv = tmp + fbytes * i + ybytes;
+        f2[i].pitch_y = f2[i].pitch_uv = g.dw;
+        f2[i].width = g.dw;
+        f2[i].height = g.dh;
+    }
+    int slot = 0;
+    int rc = upload_descriptors(ctx, h.data(), n, stream, &slot);
+    if (rc) return bail(rc);
+    (void)cudaGetLastError();
+    rc = launch_area_wide(A, ctx->ring_dev[slot], n, stream);
+    release_slot(ctx, slot, stream);
+    ctx->launches.fetch_add(1);
+    if (rc) return bail(note_error(rc, "launch_area_wide", __LINE__));
+    TsvppParams p2 = *p;  // colour stage on the intermediate: no crop, no resize
+    p2.crop_x0 = p2.crop_y0 = p2.crop_x1 = p2.crop_y1 = 0;
+    p2.dst_width = p2.dst_height = 0;
+    p2.resize_type = TSVPP_NEAREST;
+    (void)frames_on_host;  // the intermediate lives in device memory
+    rc = convert_batch_impl(ctx, f2.data(), n, &p2, out, stream, false);
+    return bail(rc);
+}
+
 // frames_on_host: the planes are device-mapped pinned host memory (zero-copy host path): keep the
 // row-segment bulk copies of the fused kernel instead of the direct kernel's 32-bit loads
 static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n, const TsvppParams *p,
@@ -1288,6 +1368,8 @@ static int convert_batch_impl(TsvppContext *ctx, const TsvppFrame *frames, int n
     const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
     std::shared_ptr<Plan> pl;
     rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+    if (rc == TSVPP_UNSUPPORTED && area_wide_applies(frames[0], *p))
+        return convert_area_wide(ctx, frames, n, p, out, stream, frames_on_host);
     if (rc) return rc;
     std::vector<FrameDev> h(n);
     for (int i = 0; i < n; ++i) {
@@ -1516,9 +1598,11 @@ static void co_drain(TsvppContext *ctx) {
         cudaEvent_t ev = nullptr;
         const bool packed = batch[i]->p.fourcc == TSVPP_UYVY || batch[i]->p.fourcc == TSVPP_YUV444;
         try {
-            if (ctx->co_memops && !packed) {
+            rc = TSVPP_UNSUPPORTED;
+            if (ctx->co_memops && !packed)
                 rc = co_launch_group(ctx, frames.data(), outs.data(), (int)frames.size(), &batch[i]->p, &seq);
-            } else {
+            if (rc == TSVPP_UNSUPPORTED && (packed || !ctx->co_memops || area_wide_applies(frames[0], batch[i]->p))) {
+                // multi-stage conversions (packed YUV, wide AREA windows) and the event fallback
                 rc = convert_batch_impl(ctx, frames.data(), (int)frames.size(), &batch[i]->p, outs.data(), ctx->co_stream, false);
                 ev = ctx->co_ev[ctx->co_evnext++ % TsvppContext::kCoEvents];
                 if (rc == TSVPP_OK && cudaEventRecord(ev, ctx->co_stream) != cudaSuccess) rc = (int)cudaGetLastError();
@@ -1669,6 +1753,17 @@ int tsvpp_batch_create(TsvppContext *ctx, const TsvppFrame *frames, int n, const
         const bool bulk = frames_bulk_ok(frames, n) && !env_int("TSVPP_FORCE_LDG", 0);
         std::shared_ptr<Plan> pl;
         rc = get_plan(ctx, frames[0], *p, bulk, &pl);
+        if (rc == TSVPP_UNSUPPORTED && area_wide_applies(frames[0], *p)) {  // multi-stage, like packed YUV
+            std::unique_ptr<TsvppBatch> b(new TsvppBatch());
+            b->ctx = ctx;
+            b->packed_yuv = true;
+            b->params = *p;
+            b->n = n;
+            b->frames.assign(frames, frames + n);
+            b->outs.assign(out, out + n);
+            *batch = b.release();
+            return TSVPP_OK;
+        }
         if (rc) return rc;
         std::unique_ptr<TsvppBatch> b(new TsvppBatch());
         b->ctx = ctx;
@@ -1899,6 +1994,11 @@ int tsvpp_describe_plan(TsvppContext *ctx, const TsvppFrame *f0, const TsvppPara
         std::shared_ptr<Plan> pl;
         const bool bulk = frames_bulk_ok(f0, 1) && !env_int("TSVPP_FORCE_LDG", 0);
         int rc = get_plan(ctx, *f0, *p, bulk, &pl);
+        if (rc == TSVPP_UNSUPPORTED && area_wide_applies(*f0, *p)) {
+            std::snprintf(buf, buflen, "kernel=area-wide resample=area (window too large for the fused stages: resize into a "
+                                       "tight NV12 intermediate, then the colour stage)");
+            return TSVPP_OK;
+        }
         if (rc) return rc;
         std::snprintf(buf, buflen, "%s", pl->desc.c_str());
         return TSVPP_OK;

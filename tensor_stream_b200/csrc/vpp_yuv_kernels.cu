@@ -343,4 +343,75 @@ int launch_packed_yuv(int yuv444, int is_float, const FrameDev *frames_dev, int 
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// AREA downscale with windows too large for the fused kernel's shared-memory stages (1080p -> 8x8: 240 x 135
+// taps per sample).  reference src/Resize.cu:160-212 (calculateAreaInterpolation, resizeNV12DownscaleAreaKernel)
+// after src/Crop.cu:4-21: one thread per output sample walks its window in the reference's order (rows outer,
+// columns inner, one FMA chain -- the chain is the arithmetic, it cannot be split across threads) and writes
+// the tight NV12 intermediate the reference's resize stage produces; the colour stage then runs on that
+// intermediate like any other frame.  Outputs of such ratios are a few hundred samples: latency, not
+// bandwidth, and irrelevant next to the source read.
+__device__ __forceinline__ int area_wide_read(const uint8_t *plane, long idx, const AreaWideParams &P, bool chroma) {
+    if (idx < 0) return 0;
+    if (P.crop) {
+        // the reference's window indexes the tight cropped copy linearly: undo that copy
+        const long size = (long)P.sw * (chroma ? P.sh / 2 : P.sh);
+        if (idx >= size) return 0;
+        const long r = idx / P.sw, c = idx - r * P.sw;
+        const long src = chroma ? ((long)(P.y0 / 2) + r) * P.pitch_uv + P.x0 + c : ((long)P.y0 + r) * P.pitch_y + P.x0 + c;
+        if (src >= (chroma ? P.plane_uv : P.plane_y)) return 0;
+        return plane[src];
+    }
+    if (idx >= (chroma ? P.plane_uv : P.plane_y)) return 0;
+    return plane[idx];
+}
+
+__global__ void __launch_bounds__(128) area_wide_kernel(const FrameDev *frames, AreaWideParams P) {
+    const FrameDev f = frames[blockIdx.y];
+    const long nl = (long)P.dw * P.dh, nc = (long)(P.dw / 2) * (P.dh / 2) * 2;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nl + nc) return;
+    const bool chroma = t >= nl;
+    int i, j, comp = 0;
+    if (!chroma) {
+        i = (int)(t / P.dw);
+        j = (int)(t - (long)i * P.dw);
+    } else {
+        const long u = t - nl;
+        comp = (int)(u & 1);
+        const long q = u >> 1;
+        i = (int)(q / (P.dw / 2));
+        j = (int)(q - (long)i * (P.dw / 2));
+    }
+    const int y = (int)floorf((float)(int)__fmul_rn(P.yr, (float)(unsigned)i));  // Resize.cu:186-190
+    const int x = (int)floorf((float)(int)__fmul_rn(P.xr, (float)(unsigned)j));
+    const float *px = P.patx + (long)(j % P.PX) * P.KX;
+    const float *py = P.paty + (long)(i % P.PY) * P.K;
+    const int ls = P.crop ? P.sw : (chroma ? P.pitch_uv : P.pitch_y);
+    const int stride = chroma ? 2 : 1;
+    const long start = (long)y * ls + (chroma ? 2 * x + comp : x);
+    const uint8_t *plane = chroma ? f.uv : f.y;
+    float sum = 0.f, div = 0.f;
+    for (int a = 0; a < P.K; ++a) {
+        const float wy = __ldg(py + a);
+        for (int b = 0; b < P.KX; ++b) {
+            const float w = __fmul_rn(__ldg(px + b), wy);
+            div = __fadd_rn(div, w);
+            sum = __fmaf_rn((float)area_wide_read(plane, start + (long)b * stride + (long)a * ls, P, chroma), w, sum);
+        }
+    }
+    sum = __fdiv_rn(sum, div);
+    uint8_t *o = static_cast<uint8_t *>(f.out);
+    if (!chroma) o[(long)i * P.dw + j] = (uint8_t)(int)sum;
+    else o[nl + (long)i * P.dw + 2 * j + comp] = (uint8_t)(int)sum;
+}
+
+int launch_area_wide(const AreaWideParams &P, const FrameDev *frames_dev, int nframes, cudaStream_t stream) {
+    const long total = (long)P.dw * P.dh + (long)(P.dw / 2) * (P.dh / 2) * 2;
+    const int threads = 128;
+    const dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)nframes);
+    area_wide_kernel<<<grid, threads, 0, stream>>>(frames_dev, P);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace tsvpp

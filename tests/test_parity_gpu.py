@@ -222,6 +222,12 @@ SYNTH += [
     ("area_pattern_longer_than_output", 2034, 260, 2034, dict(dst=(508, 64), resize_type=G.AREA, fourcc=G.NV12, planes=G.MERGED)),
     ("area_extreme_downscale", 1842, 1126, 1965, dict(dst=(42, 10), resize_type=G.AREA, fourcc=G.RGB24, planes=G.PLANAR)),
     ("area_1080p_to_16x16", 1920, 1080, 1920, dict(dst=(16, 16), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
+    # windows beyond the fused kernel's stages: the two-stage path (area_wide_kernel + colour stage)
+    ("area_wide_1080p_to_8x8", 1920, 1080, 1920, dict(dst=(8, 8), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)),
+    ("area_wide_1080p_to_2x2_hsv", 1920, 1080, 2048, dict(dst=(2, 2), resize_type=G.AREA, fourcc=G.HSV)),
+    ("area_wide_crop_nv12", 1920, 1080, 1920, dict(crop=(100, 60, 1700, 1000), dst=(4, 6), resize_type=G.AREA, fourcc=G.NV12)),
+    ("area_wide_720p_uyvy_pitch", 1280, 720, 1294, dict(dst=(6, 2), resize_type=G.AREA, fourcc=G.UYVY, normalization=True)),
+    ("area_wide_4k_to_16x16_y800", 3840, 2160, 3840, dict(dst=(16, 16), resize_type=G.AREA, fourcc=G.Y800)),
 ]
 
 
@@ -539,7 +545,8 @@ def test_prebuilt_batch_handles_every_fourcc(vp):
     frames = [_synthetic(1280, 720, seed=600 + i) for i in range(3)]
     dev = [(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda()) for y, uv in frames]
     for kw in (dict(dst=(320, 240), resize_type=G.BILINEAR, fourcc=G.BGR24, planes=G.PLANAR, normalization=True),
-               dict(dst=(320, 240), resize_type=G.AREA, fourcc=G.UYVY), dict(fourcc=G.YUV444, normalization=True)):
+               dict(dst=(320, 240), resize_type=G.AREA, fourcc=G.UYVY), dict(fourcc=G.YUV444, normalization=True),
+               dict(dst=(4, 4), resize_type=G.AREA, fourcc=G.RGB24, planes=G.MERGED)):  # two-stage wide AREA window
         from tensor_stream_b200 import vpp
         fp = _params(kw)
         shape, es = vpp.output_shape(1280, 720, fp)
@@ -553,6 +560,22 @@ def test_prebuilt_batch_handles_every_fourcc(vp):
             want = _mask_undefined(_run_oracle(y, uv, kw), kw, 1280, 720)
             assert _same(got, want), _diff_report(got, want)
         b.destroy()
+
+
+def test_wide_area_window_through_the_per_frame_coalescer(vp):
+    """The per-frame (coalesced) entry falls back to the two-stage path when the ticket path has no fused plan."""
+    from tensor_stream_b200 import vpp
+    kw = dict(dst=(4, 2), resize_type=G.AREA, fourcc=G.BGR24, planes=G.PLANAR, normalization=True)
+    fp = _params(kw)
+    shape, es = vpp.output_shape(1920, 1080, fp)
+    for seed in (910, 911):
+        y, uv = _synthetic(1920, 1080, seed=seed)
+        out = torch.zeros(shape, dtype=torch.float32, device="cuda")
+        vp.convert_coalesced(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda(), fp, out)
+        torch.cuda.synchronize()
+        want = _run_oracle(y, uv, kw)
+        assert _same(out.cpu().numpy().reshape(-1), want), _diff_report(out.cpu().numpy(), want)
+    assert "area-wide" in vp.describe_plan(torch.from_numpy(y).cuda(), torch.from_numpy(uv).cuda(), fp)
 
 
 def test_invalid_sizes_are_errors_not_crashes(vp):

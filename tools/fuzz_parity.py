@@ -26,6 +26,63 @@ def even(x):
     return max(2, int(x) & ~1)
 
 
+def pick_edge_case(rng):
+    """Tiny sources and outputs, extreme ratios, one-block crops: the clamps and the partial tiles."""
+    w, h = even(rng.choice([2, 4, 6, 8, 16, 18, 30, 34, 62, 66, 130, 258]) + rng.choice([0, 0, 2])), \
+        even(rng.choice([2, 4, 6, 8, 16, 18, 30, 34, 62, 66, 130]) + rng.choice([0, 0, 2]))
+    if rng.random() < 0.2:
+        w, h = rng.choice([(1920, 1080), (1280, 720), (2048, 64), (64, 1200)])
+    pitch = rng.choice([w, w, (w + 15) // 16 * 16, w + rng.randint(1, 40)])
+    kw = {}
+    cw, ch = w, h
+    if rng.random() < 0.4 and w >= 6 and h >= 6:
+        cw, ch = even(rng.randint(2, w - 2)), even(rng.randint(2, h - 2))
+        x0, y0 = even(rng.randint(0, w - cw)), even(rng.randint(0, h - ch))
+        if x0 + cw > w:
+            x0 = 0
+        if y0 + ch > h:
+            y0 = 0
+        kw["crop"] = (x0, y0, x0 + cw, y0 + ch)
+    if rng.random() < 0.85:
+        dw = rng.choice([2, 4, 6, 8, 10, 16, 30, 32, 34, 64, 66, 100, 128, 256, 258, 510, 1024])
+        dh = rng.choice([2, 4, 6, 8, 10, 16, 30, 32, 34, 64, 66, 100, 128, 256, 258, 510])
+        if rng.random() < 0.15:
+            dw, dh = dw + 1, dh + rng.choice([0, 1])
+        kw["dst"] = (dw, dh)
+        kw["resize_type"] = rng.choice([G.NEAREST, G.BILINEAR, G.BICUBIC, G.AREA])
+    kw["fourcc"] = rng.choice([G.RGB24, G.BGR24, G.Y800, G.HSV, G.NV12, G.UYVY, G.YUV444])
+    kw["planes"] = rng.choice([G.PLANAR, G.MERGED])
+    kw["normalization"] = rng.choice([False, True])
+    if kw["fourcc"] == G.HSV:
+        kw["normalization"] = True
+    dw, dh = kw.get("dst", (cw, ch))
+    if (dw % 2 or dh % 2) and kw["fourcc"] in (G.NV12, G.UYVY, G.YUV444):
+        kw["fourcc"] = G.BGR24
+    return w, h, pitch, kw
+
+
+def pick_wide_area_case(rng):
+    """AREA downscales of 30x and more: the narrow-tile plans and the two-stage wide-window path."""
+    w, h = rng.choice([(1920, 1080), (1280, 720), (3840, 2160), (2048, 64), (640, 1200), (1000, 600)])
+    pitch = rng.choice([w, (w + 255) // 256 * 256, w + rng.randint(1, 40)])
+    kw = {}
+    if rng.random() < 0.3:
+        cw, ch = even(rng.randint(w // 2, w - 2)), even(rng.randint(h // 2, h - 2))
+        x0, y0 = even(rng.randint(0, w - cw)), even(rng.randint(0, h - ch))
+        kw["crop"] = (x0, y0, x0 + cw, y0 + ch)
+    kw["dst"] = (rng.randint(1, 40), rng.randint(2, 24))  # one-row outputs of such ratios are TSVPP_UNSUPPORTED
+    kw["resize_type"] = G.AREA
+    kw["fourcc"] = rng.choice([G.RGB24, G.BGR24, G.Y800, G.HSV, G.NV12, G.UYVY, G.YUV444])
+    kw["planes"] = rng.choice([G.PLANAR, G.MERGED])
+    kw["normalization"] = rng.choice([False, True])
+    if kw["fourcc"] == G.HSV:
+        kw["normalization"] = True
+    dw, dh = kw["dst"]
+    if (dw % 2 or dh % 2) and kw["fourcc"] in (G.NV12, G.UYVY, G.YUV444):
+        kw["fourcc"] = G.BGR24
+    return w, h, pitch, kw
+
+
 def pick_case(rng):
     r = rng.random()
     if r < 0.25:
@@ -86,6 +143,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-cases", type=int, default=100000)
+    ap.add_argument("--profile", default="broad", choices=["broad", "edge", "wide-area"])
     args = ap.parse_args()
     import torch
     from tensor_stream_b200 import vpp
@@ -98,7 +156,7 @@ def main():
     for idx in range(args.max_cases):
         if time.time() - t0 > args.seconds:
             break
-        w, h, pitch, kw = pick_case(rng)
+        w, h, pitch, kw = {"edge": pick_edge_case, "wide-area": pick_wide_area_case, "broad": pick_case}[args.profile](rng)
         nrng = np.random.default_rng(args.seed * 1000003 + idx)
         if rng.random() < 0.3:
             y, uv = T._synthetic(w, h, args.seed * 7919 + idx, video_like=True)
