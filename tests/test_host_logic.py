@@ -121,6 +121,27 @@ def test_oracle_edge_cases_do_not_read_out_of_bounds():
             assert (w, h) == dst and out.size == 3 * w * h and oob == 0, (rt, dst, oob)
 
 
+def test_oracle_cases_found_by_the_parity_fuzzer():
+    """tools/fuzz_parity.py, round 2: (1) NV12 output with an odd width -- the reference's last column stores its V past
+    the row / past the allocation; the oracle used to corrupt the heap; (2) an AREA scale whose f32 pattern only closes
+    after thousands of rows (2034/508) used to hit the oracle's 8192-row cap."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, 256, (974, 1198), dtype=np.uint8)
+    uv = rng.integers(0, 256, (487, 1198), dtype=np.uint8)
+    for norm in (False, True):
+        out, (w, h) = O.convert(y, uv, dst=(645, 268), resize_type=O.NEAREST, fourcc=O.NV12, normalization=norm)[:2]
+        assert (w, h) == (645, 268) and out.size == 645 * 268 * 3 // 2
+    y = rng.integers(0, 256, (260, 2034), dtype=np.uint8)
+    uv = rng.integers(0, 256, (130, 2034), dtype=np.uint8)
+    out, (w, h) = O.convert(y, uv, dst=(508, 64), resize_type=O.AREA, fourcc=O.NV12)[:2]
+    assert (w, h) == (508, 64)
+    # a pattern as long as the output is all the kernel can index: the long scale agrees with the full pattern on
+    # the rows both have
+    full = O.area_pattern(np.float32(2034) / np.float32(508), max_rows=60000)
+    assert full.shape[0] > 508
+
+
 def test_stream_sharding_is_a_partition():
     from tensor_stream_b200 import sharding as S
     for world in (1, 2, 4, 8):
