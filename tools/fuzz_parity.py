@@ -138,12 +138,52 @@ def pick_case(rng):
     return w, h, pitch, kw
 
 
+def run_api(v, api, y, uv, kw, pitch):
+    """The same conversion through one of the library's entry points; returns the flat result(s)."""
+    import torch
+    from tensor_stream_b200 import vpp
+    h, w = y.shape
+    fp = T._params(kw)
+    if api == "device":
+        return [T._run_cuda(v, y, uv, kw, pitch)]
+    if api in ("host", "pinned"):
+        py = np.zeros((h, pitch), dtype=np.uint8)
+        puv = np.zeros((h // 2, pitch), dtype=np.uint8)
+        py[:, :w] = y
+        puv[:, :w] = uv
+        if api == "pinned":
+            ty, tuv = torch.from_numpy(py).pin_memory(), torch.from_numpy(puv).pin_memory()
+            outs = v.convert_batch_host([(ty, tuv), (ty, tuv)], fp, w, h)
+        else:
+            outs = v.convert_batch_host([(py, puv), (py, puv)], fp, w, h)
+        return [np.asarray(o).reshape(-1) for o in outs]
+    ty, tuv, _ = T._to_dev(y, uv, pitch)
+    shape, es = vpp.output_shape(w, h, fp)
+    dt = torch.float32 if es == 4 else torch.uint8
+    if api == "batch":
+        outs = [torch.zeros(shape, dtype=dt, device="cuda") for _ in range(3)]
+        b = v.make_batch([(ty, tuv)] * 3, fp, outs, widths=(w, h))
+        b.run()
+        torch.cuda.synchronize()
+        b.destroy()
+        return [o.cpu().numpy().reshape(-1) for o in outs]
+    if api == "coalesced":
+        out = torch.zeros(shape, dtype=dt, device="cuda")
+        v.convert_coalesced(ty, tuv, fp, out, width=w, height=h)
+        torch.cuda.synchronize()
+        return [out.cpu().numpy().reshape(-1)]
+    raise ValueError(api)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-cases", type=int, default=100000)
     ap.add_argument("--profile", default="broad", choices=["broad", "edge", "wide-area"])
+    ap.add_argument("--api", default="device", choices=["device", "host", "pinned", "batch", "coalesced", "all"],
+                    help="entry point: tsvpp_convert_batch (default), the host-buffer entry with pageable or pinned buffers, "
+                         "a prebuilt batch, the per-frame coalescer, or a random one per case")
     args = ap.parse_args()
     import torch
     from tensor_stream_b200 import vpp
@@ -170,11 +210,13 @@ def main():
             oracle_err = None
         except Exception as e:  # noqa: BLE001
             want, oracle_err = None, e
+        api = args.api if args.api != "all" else rng.choice(["device", "host", "pinned", "batch", "coalesced"])
+        tag += " api=" + api
         try:
-            got = T._run_cuda(v, y, uv, kw, pitch)
-            cuda_err = None
+            gots = run_api(v, api, y, uv, kw, pitch)
+            got, cuda_err = gots[0], None
         except vpp.VppError as e:
-            got, cuda_err = None, e
+            gots, got, cuda_err = [], None, e
         if cuda_err is not None or oracle_err is not None:
             if cuda_err is not None and oracle_err is not None:
                 both_rejected += 1
@@ -189,13 +231,16 @@ def main():
         except Exception:  # noqa: BLE001
             k = "no fused plan"
         kernels[k] = kernels.get(k, 0) + 1
-        a = T._mask_undefined(got, kw, w, h)
         b = T._mask_undefined(want, kw, w, h)
-        if T._same(a, b):
-            ok += 1
-        else:
-            bad += 1
-            print("MISMATCH %s [%s]: %s" % (tag, k, T._diff_report(np.asarray(a), np.asarray(b))), flush=True)
+        good = True
+        for got in gots:
+            a = T._mask_undefined(got, kw, w, h)
+            if not T._same(a, b):
+                good = False
+                print("MISMATCH %s [%s]: %s" % (tag, k, T._diff_report(np.asarray(a), np.asarray(b))), flush=True)
+                break
+        ok += good
+        bad += not good
     print("cases %d ok %d mismatches %d rejected-by-one-side %d rejected-by-both %d in %.0f s" %
           (n, ok, bad, rejected, both_rejected, time.time() - t0))
     for k in sorted(kernels, key=kernels.get, reverse=True):
