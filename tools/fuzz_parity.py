@@ -42,6 +42,9 @@ def pick_edge_case(rng):
             x0 = 0
         if y0 + ch > h:
             y0 = 0
+        if rng.random() < 0.25:
+            x0 += 1 if x0 + cw + 1 <= w else 0
+            y0 += 1 if y0 + ch + 1 <= h and rng.random() < 0.5 else 0
         kw["crop"] = (x0, y0, x0 + cw, y0 + ch)
     if rng.random() < 0.85:
         dw = rng.choice([2, 4, 6, 8, 10, 16, 30, 32, 34, 64, 66, 100, 128, 256, 258, 510, 1024])
@@ -108,6 +111,9 @@ def pick_case(rng):
             x0 = 0
         if y0 + ch > h:
             y0 = 0
+        if rng.random() < 0.25:  # odd origins are defined behaviour in the reference (Crop.cu:9-16), even sizes only
+            x0 += 1 if x0 + cw + 1 <= w else 0
+            y0 += 1 if y0 + ch + 1 <= h and rng.random() < 0.5 else 0
         kw["crop"] = (x0, y0, x0 + cw, y0 + ch)
     dr = rng.random()
     if dr < 0.15:
